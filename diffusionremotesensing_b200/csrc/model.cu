@@ -1,0 +1,686 @@
+// DrsModel: state_dict -> bf16 UMMA weight tiles + K-block programs + folded eval-BatchNorm vectors.
+// Reference modules restated here (shapes and key names): UNet_model_superres.py:57-379,
+// UNet_model_SAR_TO_NDVI.py:263-370, generate_new_imgs/UNet_model_generation.py:226-329.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <set>
+
+#include "engine.cuh"
+
+namespace drs {
+
+// ------------------------------------------------------------------------------------------------
+// errors / device memory
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return DRS_E_CUDA;
+}
+
+int DevMem::alloc(size_t n) {
+  release();
+  if (n == 0) n = 16;
+  DRS_CUDA(cudaMalloc(&p, n));
+  bytes = n;
+  return DRS_OK;
+}
+int DevMem::upload(const void* host, size_t n) {
+  DRS_TRY(alloc(n));
+  if (n) DRS_CUDA(cudaMemcpy(p, host, n, cudaMemcpyHostToDevice));
+  return DRS_OK;
+}
+void DevMem::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+static inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);                                                       // RNE
+  return static_cast<uint16_t>(u >> 16);
+}
+
+static int pow2_at_least(int v, int lo) {
+  int p = lo;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+struct Tap {
+  int ky, kx;       // weight tap
+  int dx, dy;       // tile-origin shift (coordinates 1 and 3 of the TMA box)
+  int py, px;       // parity selectors of a stride-2 view
+  int group;        // ConvTranspose output phase (a << 1 | b), else 0
+};
+
+static std::vector<Tap> taps_of(int kind) {
+  std::vector<Tap> t;
+  switch (kind) {
+    case CONV_3x3:
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) t.push_back({ky, kx, kx - 1, ky - 1, 0, 0, 0});
+      break;
+    case CONV_3x3_S2: {
+      // input row 2*oy + ky - 1 seen through the view [H/2][2]: ky=0 -> (oy-1, 1), ky=1 -> (oy, 0), ky=2 -> (oy, 1)
+      const int d[3] = {-1, 0, 0}, p[3] = {1, 0, 1};
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) t.push_back({ky, kx, d[kx], d[ky], p[ky], p[kx], 0});
+      break;
+    }
+    case CONV_1x1:
+      t.push_back({0, 0, 0, 0, 0, 0, 0});
+      break;
+    case CONV_2x2_S2:
+      for (int ky = 0; ky < 2; ++ky)
+        for (int kx = 0; kx < 2; ++kx) t.push_back({ky, kx, 0, 0, ky, kx, 0});
+      break;
+    case CONV_T3x3_S2: {
+      // ConvTranspose2d(k=3, s=2, p=1, op=1): out[2i+a] takes (ky=1, i) for a=0 and (ky=2, i), (ky=0, i+1) for a=1
+      struct P { int k, d; };
+      const std::vector<P> ph[2] = {{{1, 0}}, {{2, 0}, {0, 1}}};
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b)
+          for (const P& y : ph[a])
+            for (const P& x : ph[b]) t.push_back({y.k, x.k, x.d, y.d, 0, 0, (a << 1) | b});
+      break;
+    }
+  }
+  return t;
+}
+
+struct Builder {
+  DrsModel* m;
+  explicit Builder(DrsModel* mm) : m(mm) {}
+
+  const std::vector<float>* get(const std::string& key, size_t numel) {
+    auto it = m->sd.find(key);
+    if (it == m->sd.end()) {
+      set_error("state_dict entry '%s' is missing", key.c_str());
+      return nullptr;
+    }
+    if (it->second.size() != numel) {
+      set_error("state_dict entry '%s' has %zu elements, expected %zu", key.c_str(), it->second.size(), numel);
+      return nullptr;
+    }
+    return &it->second;
+  }
+
+  long push(const float* v, size_t n) {
+    while (m->fblob.size() % 4) m->fblob.push_back(0.f);
+    const long off = static_cast<long>(m->fblob.size());
+    m->fblob.insert(m->fblob.end(), v, v + n);
+    return off;
+  }
+  long push(const std::vector<float>& v) { return push(v.data(), v.size()); }
+
+  // eval BatchNorm folded behind a conv bias: y = acc * s + (cb * s + beta - mean * s)
+  bool bn_fold(const std::string& bn, const std::vector<float>* cb, int C, std::vector<float>& s,
+               std::vector<float>& b) {
+    const auto* w = get(bn + ".weight", C);
+    const auto* be = get(bn + ".bias", C);
+    const auto* mu = get(bn + ".running_mean", C);
+    const auto* var = get(bn + ".running_var", C);
+    if (!w || !be || !mu || !var) return false;
+    s.resize(C);
+    b.resize(C);
+    for (int c = 0; c < C; ++c) {
+      const float sc = (*w)[c] / sqrtf((*var)[c] + 1e-5f);
+      s[c] = sc;
+      b[c] = (cb ? (*cb)[c] : 0.f) * sc + ((*be)[c] - (*mu)[c] * sc);
+    }
+    return true;
+  }
+
+  // Appends the K-blocks of `terms` for every N-split and packs the weight tiles.
+  bool build(GemmSpec& g, const std::vector<ConvTerm>& terms) {
+    g.nsplit = g.OC / g.n_sub;
+    if (g.nsplit * g.n_sub != g.OC || g.n_sub % 16) {
+      set_error("%s: bad split OC=%d n_sub=%d", g.name.c_str(), g.OC, g.n_sub);
+      return false;
+    }
+    int max_col = 0;
+    g.kblocks.clear();
+    for (int s = 0; s < g.nsplit; ++s) {
+      std::set<int> seen;
+      int count = 0;
+      for (const ConvTerm& t : terms) {
+        const int ck = t.C >= 64 ? 64 : t.C;
+        if (ck != 16 && ck != 32 && ck != 64) {
+          set_error("%s: unsupported source channel count %d", g.name.c_str(), t.C);
+          return false;
+        }
+        if (t.C % ck) {
+          set_error("%s: channels %d not a multiple of %d", g.name.c_str(), t.C, ck);
+          return false;
+        }
+        g.src_C[t.src] = t.C;
+        g.src_ck[t.src] = ck;
+        g.src_stride2[t.src] = (t.kind == CONV_3x3_S2 || t.kind == CONV_2x2_S2) ? 1 : 0;
+        g.n_src = std::max(g.n_src, t.src + 1);
+        const int n = g.n_sub * static_cast<int>(t.stack.size());
+        if (n > 256) {
+          set_error("%s: MMA N=%d exceeds 256", g.name.c_str(), n);
+          return false;
+        }
+        const int row_bytes = ck * 2;
+        const uint32_t mask = static_cast<uint32_t>(row_bytes / 16 - 1);
+        const bool transposed = (t.kind == CONV_T3x3_S2);
+        const int kh = (t.kind == CONV_1x1) ? 1 : (t.kind == CONV_2x2_S2 ? 2 : 3);
+        for (const Tap& tp : taps_of(t.kind)) {
+          for (int c0 = 0; c0 < t.C; c0 += ck) {
+            KBlock kb{};
+            kb.c = tp.px * t.C + c0;
+            kb.dx = static_cast<int16_t>(tp.dx);
+            kb.dy = static_cast<int16_t>(tp.dy);
+            kb.py = static_cast<int16_t>(tp.py);
+            kb.src = static_cast<uint8_t>(t.src);
+            kb.ck = static_cast<uint8_t>(ck);
+            kb.n = static_cast<uint16_t>(n);
+            const int col = (t.col_slot + tp.group) * g.n_sub;
+            kb.col = static_cast<uint16_t>(col);
+            kb.init = seen.insert(col).second ? 1 : 0;
+            max_col = std::max(max_col, col + n);
+            kb.b_bytes = static_cast<uint32_t>(n * row_bytes);
+            while (m->wblob.size() % 128) m->wblob.push_back(0);
+            kb.b_off = static_cast<uint32_t>(m->wblob.size());
+            m->wblob.resize(m->wblob.size() + kb.b_bytes);
+            uint8_t* tile = m->wblob.data() + kb.b_off;
+            for (int r = 0; r < n; ++r) {
+              const WeightRef& wr = t.stack[r / g.n_sub];
+              const int oc = s * g.n_sub + (r % g.n_sub);
+              for (int k = 0; k < ck; ++k) {
+                const int ci = wr.ci_off + c0 + k;
+                float v;
+                if (transposed)
+                  v = wr.w[((static_cast<size_t>(ci) * wr.oc + oc) * 3 + tp.ky) * 3 + tp.kx];
+                else
+                  v = wr.w[((static_cast<size_t>(oc) * wr.cin_total + ci) * kh + tp.ky) * kh + tp.kx];
+                uint32_t o = static_cast<uint32_t>(r * row_bytes + k * 2);
+                o ^= ((o >> 7) & mask) << 4;  // Swizzle<log2(row_bytes/16), 4, 3>
+                const uint16_t h = f32_to_bf16(v);
+                memcpy(tile + o, &h, 2);
+              }
+            }
+            g.max_b_bytes = std::max(g.max_b_bytes, static_cast<int>(kb.b_bytes));
+            g.max_a_bytes = std::max(g.max_a_bytes, kTileM * row_bytes);
+            g.kblocks.push_back(kb);
+            ++count;
+          }
+        }
+      }
+      if (s == 0) g.nkb = count;
+    }
+    if (g.nkb > kMaxKBlocks) {
+      set_error("%s: %d K-blocks exceed the limit %d", g.name.c_str(), g.nkb, kMaxKBlocks);
+      return false;
+    }
+    if (max_col > 512) {
+      set_error("%s: %d accumulator columns exceed TMEM", g.name.c_str(), max_col);
+      return false;
+    }
+    g.tmem_cols = pow2_at_least(max_col, 32);
+    g.kb_dev_off = m->kb_all.size();
+    m->kb_all.insert(m->kb_all.end(), g.kblocks.begin(), g.kblocks.end());
+    return true;
+  }
+};
+
+static WeightRef wref(const std::vector<float>* w, int oc, int cin_total, int ci_off = 0) {
+  WeightRef r;
+  r.w = w->data();
+  r.oc = oc;
+  r.cin_total = cin_total;
+  r.ci_off = ci_off;
+  return r;
+}
+
+static ConvTerm term(int src, int C, int kind, std::vector<WeightRef> stack, int slot = 0) {
+  ConvTerm t;
+  t.src = src;
+  t.C = C;
+  t.kind = kind;
+  t.stack = std::move(stack);
+  t.col_slot = slot;
+  return t;
+}
+
+static int n_sub_for(int OC) { return OC > 128 ? 128 : OC; }
+
+// ResConvBlock (UNet_model_superres.py:110-172) as two launches.
+static bool build_res_block(Builder& B, const std::string& p, int cin, int cout, bool has_skip, const std::string& in,
+                            const std::string& mid, const std::string& out, int te_off) {
+  DrsModel* m = B.m;
+  // launch 1: h = relu(bn1(conv1(x))) [+ conv_skip(x)] + relu(time_mlp(t))
+  {
+    GemmSpec g;
+    g.name = p + ".conv1";
+    g.src_name[0] = in;
+    g.out_name = mid;
+    g.OC = cout;
+    g.n_sub = has_skip ? std::min(cout, 128) : n_sub_for(cout);
+    g.flags = F_RELU | F_TE;
+    g.te_off = te_off;
+    const auto* w1 = B.get(p + ".conv1.0.weight", static_cast<size_t>(cout) * cin * 9);
+    const auto* b1 = B.get(p + ".conv1.0.bias", cout);
+    if (!w1 || !b1) return false;
+    std::vector<float> s, b;
+    if (!B.bn_fold(p + ".batch_norm1", b1, cout, s, b)) return false;
+    g.scale = B.push(s);
+    g.bias = B.push(b);
+    std::vector<WeightRef> stack{wref(w1, cout, cin)};
+    if (has_skip) {
+      const auto* ws = B.get(p + ".conv_upsampled_lr_img.weight", static_cast<size_t>(cout) * cin * 9);
+      const auto* bs = B.get(p + ".conv_upsampled_lr_img.bias", cout);
+      if (!ws || !bs) return false;
+      stack.push_back(wref(ws, cout, cin));
+      g.flags |= F_DUAL_POST;
+      g.bias2 = B.push(*bs);
+      g.col2 = g.n_sub;
+    }
+    if (!B.build(g, {term(0, cin, CONV_3x3, stack)})) return false;
+    m->gemms.push_back(std::move(g));
+  }
+  // launch 2: out = relu(bn2(conv2(h)) + bn3(shortcut1x1(x)))
+  {
+    GemmSpec g;
+    g.name = p + ".conv2";
+    g.src_name[0] = mid;
+    g.src_name[1] = in;
+    g.out_name = out;
+    g.OC = cout;
+    g.n_sub = n_sub_for(cout);
+    g.flags = F_RELU | F_DUAL_PRE;
+    g.col2 = g.n_sub;
+    const auto* w2 = B.get(p + ".conv2.0.weight", static_cast<size_t>(cout) * cout * 9);
+    const auto* b2 = B.get(p + ".conv2.0.bias", cout);
+    const auto* w3 = B.get(p + ".shortcut_conv.0.weight", static_cast<size_t>(cout) * cin);
+    const auto* b3 = B.get(p + ".shortcut_conv.0.bias", cout);
+    if (!w2 || !b2 || !w3 || !b3) return false;
+    std::vector<float> s2, bb2, s3, bb3;
+    if (!B.bn_fold(p + ".batch_norm2", b2, cout, s2, bb2)) return false;
+    if (!B.bn_fold(p + ".shortcut_batch_norm", b3, cout, s3, bb3)) return false;
+    for (int c = 0; c < cout; ++c) bb2[c] += bb3[c];
+    g.scale = B.push(s2);
+    g.bias = B.push(bb2);
+    g.scale2 = B.push(s3);
+    if (!B.build(g, {term(0, cout, CONV_3x3, {wref(w2, cout, cout)}, 0),
+                     term(1, cin, CONV_1x1, {wref(w3, cout, cin)}, 1)}))
+      return false;
+    m->gemms.push_back(std::move(g));
+  }
+  return true;
+}
+
+static bool build_time_mlp(Builder& B, const std::string& p, int C, TimeMlp& t) {
+  const auto* w1 = B.get(p + ".time_mlp.0.weight", static_cast<size_t>(C) * 100);
+  const auto* b1 = B.get(p + ".time_mlp.0.bias", C);
+  const auto* w2 = B.get(p + ".time_mlp.2.weight", static_cast<size_t>(C) * C);
+  const auto* b2 = B.get(p + ".time_mlp.2.bias", C);
+  if (!w1 || !b1 || !w2 || !b2) return false;
+  t.C = C;
+  t.w1 = B.push(*w1);
+  t.b1 = B.push(*b1);
+  t.w2 = B.push(*w2);
+  t.b2 = B.push(*b2);
+  return true;
+}
+
+static bool build_small(Builder& B, const std::string& p, int cout, int cin, SmallConv& c) {
+  const auto* w = B.get(p + ".weight", static_cast<size_t>(cout) * cin * 9);
+  const auto* b = B.get(p + ".bias", cout);
+  if (!w || !b) return false;
+  c.w = B.push(*w);
+  c.b = B.push(*b);
+  c.cin = cin;
+  c.cout = cout;
+  return true;
+}
+
+static bool build_model(DrsModel* m) {
+  Builder B(m);
+  const DrsModelDesc& d = m->desc;
+  const int down[5] = {16, 32, 64, 128, 256};
+
+  // ---- time-table row layout -------------------------------------------------------------------
+  int off = 0;
+  const int mlp_C[7] = {32, 64, 128, 256, 256, 128, 64};
+  for (int i = 0; i < 7; ++i) {
+    m->mlps[i].te_off = off;
+    off += mlp_C[i];
+  }
+  for (int i = 4; i < 7; ++i) {
+    m->mlps[i].pre_off = off;
+    off += 9 * mlp_C[i];
+  }
+  m->te_stride = off;
+
+  // ---- CUDA-core pieces ------------------------------------------------------------------------
+  if (!build_small(B, "conv0", 16, d.x_channels, m->conv0)) return false;
+  m->has_cond = (d.kind != DRS_MODEL_GENERATION);
+  if (m->has_cond) {
+    const std::string enc = (d.kind == DRS_MODEL_SUPERRES) ? "LR_encoder" : "SAR_encoder";
+    const std::string cc = (d.kind == DRS_MODEL_SUPERRES) ? "conv_upsampled_lr_img" : "conv_SAR_img";
+    const int Cc = d.cond_channels;
+    if (Cc < 1 || Cc > 4) {
+      set_error("cond_channels %d not in [1,4]", Cc);
+      return false;
+    }
+    for (int i = 0; i < 3; ++i) {
+      if (!build_small(B, enc + ".blocks." + std::to_string(i) + ".conv1", Cc, Cc, m->enc[2 * i])) return false;
+      if (!build_small(B, enc + ".blocks." + std::to_string(i) + ".conv2", Cc, Cc, m->enc[2 * i + 1])) return false;
+    }
+    if (!build_small(B, enc + ".conv_out", Cc, Cc, m->enc[6])) return false;
+    if (!build_small(B, cc, 16, Cc, m->cond_conv)) return false;
+  }
+  {
+    std::vector<float> f(50);
+    auto it = m->sd.find("pos_encoding.inv_freq");
+    if (it != m->sd.end() && it->second.size() == 50) {
+      f = it->second;
+    } else {
+      // 1 / 10000^(2j/100), the fp32 evaluation order of UNet_model_superres.py:329-331
+      for (int j = 0; j < 50; ++j) f[j] = 1.0f / powf(10000.0f, static_cast<float>(2 * j) / 100.0f);
+    }
+    m->inv_freq = B.push(f);
+  }
+  if (d.kind == DRS_MODEL_GENERATION && d.num_classes > 0) {
+    const auto* e = B.get("label_emb.weight", static_cast<size_t>(d.num_classes) * 100);
+    if (!e) return false;
+    m->label_emb = B.push(*e);
+  }
+
+  // ---- time MLPs -------------------------------------------------------------------------------
+  for (int i = 0; i < 3; ++i)
+    if (!build_time_mlp(B, "conv_blocks." + std::to_string(i), mlp_C[i], m->mlps[i])) return false;
+  if (!build_time_mlp(B, "bottle_neck", 256, m->mlps[3])) return false;
+  for (int i = 0; i < 3; ++i) {
+    TimeMlp& t = m->mlps[4 + i];
+    const int C = mlp_C[4 + i];
+    if (!build_time_mlp(B, "ups." + std::to_string(i), C, t)) return false;
+    // tap-major fp32 copy of ups.i.conv.weight: Wt[(ky*3+kx)*C + oc][ci]
+    const auto* w = B.get("ups." + std::to_string(i) + ".conv.weight", static_cast<size_t>(C) * C * 9);
+    if (!w) return false;
+    std::vector<float> wt(static_cast<size_t>(9) * C * C);
+    for (int oc = 0; oc < C; ++oc)
+      for (int ci = 0; ci < C; ++ci)
+        for (int k = 0; k < 9; ++k)
+          wt[(static_cast<size_t>(k) * C + oc) * C + ci] = (*w)[(static_cast<size_t>(oc) * C + ci) * 9 + k];
+    t.wtap = B.push(wt);
+  }
+
+  // ---- encoder path ----------------------------------------------------------------------------
+  const char* lvl_in[4] = {"h0", "d0", "d1", "d2"};
+  const char* lvl_mid[4] = {"b0.h", "b1.h", "b2.h", "bn.h"};
+  const char* lvl_out[4] = {"b0.out", "b1.out", "b2.out", "bn.out"};
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = "conv_blocks." + std::to_string(i);
+    if (!build_res_block(B, p, down[i], down[i + 1], i == 0, lvl_in[i], lvl_mid[i], lvl_out[i], m->mlps[i].te_off))
+      return false;
+    GemmSpec g;
+    g.name = "downs." + std::to_string(i);
+    g.src_name[0] = lvl_out[i];
+    g.out_name = lvl_in[i + 1];
+    const int C = down[i + 1];
+    g.OC = C;
+    g.n_sub = n_sub_for(C);
+    const auto* w = B.get(g.name + ".weight", static_cast<size_t>(C) * C * 9);
+    const auto* b = B.get(g.name + ".bias", C);
+    if (!w || !b) return false;
+    g.bias = B.push(*b);
+    if (!B.build(g, {term(0, C, CONV_3x3_S2, {wref(w, C, C)})})) return false;
+    m->gemms.push_back(std::move(g));
+  }
+  if (!build_res_block(B, "bottle_neck", 128, 256, false, "d2", "bn.h", "bn.out", m->mlps[3].te_off)) return false;
+
+  // ---- decoder path ----------------------------------------------------------------------------
+  const int up[4] = {256, 128, 64, 32};
+  std::string xin = "bn.out";
+  for (int i = 0; i < 3; ++i) {
+    const int C = up[i], Ch = up[i + 1];
+    const std::string si = std::to_string(i);
+    const std::string skip = lvl_out[2 - i];
+    // gating_signal: relu(bn(conv1x1(x)))   (UNet_model_superres.py:209-225)
+    {
+      GemmSpec g;
+      g.name = "gating_signals." + si;
+      g.src_name[0] = xin;
+      g.out_name = "g" + si;
+      g.OC = Ch;
+      g.n_sub = n_sub_for(Ch);
+      g.flags = F_RELU;
+      const auto* w = B.get(g.name + ".conv.weight", static_cast<size_t>(Ch) * C);
+      const auto* b = B.get(g.name + ".conv.bias", Ch);
+      if (!w || !b) return false;
+      std::vector<float> s, bb;
+      if (!B.bn_fold(g.name + ".batch_norm", b, Ch, s, bb)) return false;
+      g.scale = B.push(s);
+      g.bias = B.push(bb);
+      if (!B.build(g, {term(0, C, CONV_1x1, {wref(w, Ch, C)})})) return false;
+      m->gemms.push_back(std::move(g));
+    }
+    // attention gate map: psi = sigmoid(w_psi . relu(W_g g + W_x x) + b_psi)   (:101-104)
+    const std::string ab = "attention_blocks." + si;
+    {
+      GemmSpec g;
+      g.name = ab + ".psi";
+      g.src_name[0] = "g" + si;
+      g.src_name[1] = skip;
+      g.out_name = "psi" + si;
+      g.epi_kind = EPI_PSI;
+      g.OC = Ch;
+      g.n_sub = Ch;
+      const auto* wg = B.get(ab + ".w_g.0.weight", static_cast<size_t>(Ch) * Ch);
+      const auto* bg = B.get(ab + ".w_g.0.bias", Ch);
+      const auto* wx = B.get(ab + ".w_x.0.weight", static_cast<size_t>(Ch) * Ch * 4);
+      const auto* bx = B.get(ab + ".w_x.0.bias", Ch);
+      const auto* wp = B.get(ab + ".psi.0.weight", Ch);
+      const auto* bp = B.get(ab + ".psi.0.bias", 1);
+      if (!wg || !bg || !wx || !bx || !wp || !bp) return false;
+      std::vector<float> bsum(Ch);
+      for (int c = 0; c < Ch; ++c) bsum[c] = (*bg)[c] + (*bx)[c];
+      g.bias = B.push(bsum);
+      g.wvec = B.push(*wp);
+      g.bvec = B.push(*bp);
+      g.nvec = 1;
+      if (!B.build(g, {term(0, Ch, CONV_1x1, {wref(wg, Ch, Ch)}, 0), term(1, Ch, CONV_2x2_S2, {wref(wx, Ch, Ch)}, 0)}))
+        return false;
+      m->gemms.push_back(std::move(g));
+    }
+    // attention result: bn(conv1x1(psi_up * x)) = bn(psi_up * (W x) + b)   (:105-107)
+    {
+      GemmSpec g;
+      g.name = ab + ".result";
+      g.src_name[0] = skip;
+      g.src_name[1] = "psi" + si;  // not a TMA source: row scale
+      g.out_name = "att" + si;
+      g.OC = Ch;
+      g.n_sub = n_sub_for(Ch);
+      g.flags = F_ROWSCALE;
+      const auto* w = B.get(ab + ".result.0.weight", static_cast<size_t>(Ch) * Ch);
+      const auto* b = B.get(ab + ".result.0.bias", Ch);
+      if (!w || !b) return false;
+      std::vector<float> s, bb;
+      if (!B.bn_fold(ab + ".result.1", b, Ch, s, bb)) return false;
+      g.scale = B.push(s);
+      g.bias = B.push(bb);
+      if (!B.build(g, {term(0, Ch, CONV_1x1, {wref(w, Ch, Ch)})})) return false;
+      g.n_src = 1;
+      m->gemms.push_back(std::move(g));
+    }
+    // UpConvBlock conv: relu(bn(conv3x3(x + relu(time_mlp(t)))))   (:197-205)
+    const std::string ub = "ups." + si;
+    {
+      GemmSpec g;
+      g.name = ub + ".conv";
+      g.src_name[0] = xin;
+      g.out_name = "uc" + si;
+      g.OC = C;
+      g.n_sub = n_sub_for(C);
+      g.flags = F_RELU | F_PRE;
+      g.pre_off = m->mlps[4 + i].pre_off;
+      const auto* w = B.get(ub + ".conv.weight", static_cast<size_t>(C) * C * 9);
+      const auto* b = B.get(ub + ".conv.bias", C);
+      if (!w || !b) return false;
+      std::vector<float> s, bb;
+      if (!B.bn_fold(ub + ".batch_norm", b, C, s, bb)) return false;
+      g.scale = B.push(s);
+      g.bias = B.push(bb);
+      if (!B.build(g, {term(0, C, CONV_3x3, {wref(w, C, C)})})) return false;
+      m->gemms.push_back(std::move(g));
+    }
+    // UpConvBlock transform: ConvTranspose2d(3, s2, p1, op1) as four sub-pixel phases   (:206)
+    {
+      GemmSpec g;
+      g.name = ub + ".transform";
+      g.src_name[0] = "uc" + si;
+      g.out_name = "ut" + si;
+      g.OC = C;
+      g.n_sub = std::min(C, 64);
+      g.n_groups = 4;
+      g.oscale = 2;
+      const auto* w = B.get(ub + ".transform.weight", static_cast<size_t>(C) * C * 9);
+      const auto* b = B.get(ub + ".transform.bias", C);
+      if (!w || !b) return false;
+      g.bias = B.push(*b);
+      if (!B.build(g, {term(0, C, CONV_T3x3_S2, {wref(w, C, C)})})) return false;
+      m->gemms.push_back(std::move(g));
+    }
+    // up_convs: conv3x3(cat[x_up, att]) with the concatenation as split-K over two sources   (:376-377)
+    {
+      GemmSpec g;
+      g.name = "up_convs." + si;
+      g.src_name[0] = "ut" + si;
+      g.src_name[1] = "att" + si;
+      const int Cin = C + Ch;
+      const auto* w = B.get(g.name + ".weight", static_cast<size_t>(Ch) * Cin * 9);
+      const auto* b = B.get(g.name + ".bias", Ch);
+      if (!w || !b) return false;
+      g.OC = Ch;
+      g.bias = B.push(*b);
+      if (i < 2) {
+        g.out_name = "x" + si;
+        g.n_sub = n_sub_for(Ch);
+      } else {
+        // last stage: the 1x1 output conv (UNet_model_superres.py:379) runs on the fp32 accumulator
+        g.epi_kind = EPI_OUT;
+        g.n_sub = Ch;
+        const auto* wo = B.get("output.weight", static_cast<size_t>(d.out_channels) * Ch);
+        const auto* bo = B.get("output.bias", d.out_channels);
+        if (!wo || !bo) return false;
+        if (d.out_channels > 4) {
+          set_error("out_channels %d > 4", d.out_channels);
+          return false;
+        }
+        g.wvec = B.push(*wo);
+        g.bvec = B.push(*bo);
+        g.nvec = d.out_channels;
+      }
+      if (!B.build(g, {term(0, C, CONV_3x3, {wref(w, Ch, Cin, 0)}, 0), term(1, Ch, CONV_3x3, {wref(w, Ch, Cin, C)}, 0)}))
+        return false;
+      m->gemms.push_back(std::move(g));
+    }
+    xin = "x" + si;
+  }
+  return true;
+}
+
+int model_create(const DrsModelDesc* desc, const DrsTensor* tensors, int n_tensors, int device, DrsModel** out) {
+  if (!desc || !out || (!tensors && n_tensors > 0)) {
+    set_error("drs_model_create: null argument");
+    return DRS_E_INVALID;
+  }
+  if (desc->kind < 0 || desc->kind > 2 || desc->x_channels < 1 || desc->x_channels > 4 || desc->out_channels < 1) {
+    set_error("drs_model_create: bad descriptor");
+    return DRS_E_INVALID;
+  }
+  DRS_CUDA(cudaSetDevice(device));
+  int major = 0;
+  DRS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) {
+    set_error("device %d has compute capability %d.x; this library is sm_100a only", device, major);
+    return DRS_E_INVALID;
+  }
+  std::unique_ptr<DrsModel> m(new DrsModel());
+  m->desc = *desc;
+  m->device = device;
+  for (int i = 0; i < n_tensors; ++i) {
+    if (!tensors[i].name || (!tensors[i].data && tensors[i].numel > 0)) {
+      set_error("drs_model_create: tensor %d is null", i);
+      return DRS_E_INVALID;
+    }
+    m->sd[tensors[i].name].assign(tensors[i].data, tensors[i].data + tensors[i].numel);
+  }
+  if (!build_model(m.get())) return DRS_E_MISSING;
+  DRS_TRY(m->d_fblob.upload(m->fblob.data(), m->fblob.size() * sizeof(float)));
+  DRS_TRY(m->d_wblob.upload(m->wblob.data(), m->wblob.size()));
+  DRS_TRY(m->d_kblocks.upload(m->kb_all.data(), m->kb_all.size() * sizeof(KBlock)));
+  const int r = conv_gemm_set_smem_limits();
+  if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "cudaFuncSetAttribute(conv_gemm_kernel)");
+  // the host copy of the state_dict is no longer needed
+  m->sd.clear();
+  std::vector<uint8_t>().swap(m->wblob);
+  *out = m.release();
+  return DRS_OK;
+}
+
+// Single-layer model for drs_debug_conv2d.
+int build_debug_conv(DrsModel* m, const float* w, const float* bias, const float* scale, const float* shift, int Cin,
+                     int Cout, int kind, int relu) {
+  Builder B(m);
+  GemmSpec g;
+  g.name = "debug_conv";
+  g.src_name[0] = "in";
+  g.out_name = "out";
+  g.OC = Cout;
+  g.flags = relu ? F_RELU : 0;
+  std::vector<float> s(Cout, 1.f), b(Cout, 0.f);
+  for (int c = 0; c < Cout; ++c) {
+    const float sc = scale ? scale[c] : 1.f;
+    s[c] = sc;
+    b[c] = (bias ? bias[c] : 0.f) * sc + (shift ? shift[c] : 0.f);
+  }
+  g.scale = B.push(s);
+  g.bias = B.push(b);
+  WeightRef wr;
+  wr.w = w;
+  wr.oc = Cout;
+  wr.cin_total = Cin;
+  if (kind == CONV_T3x3_S2) {
+    g.n_sub = std::min(Cout, 64);
+    g.n_groups = 4;
+    g.oscale = 2;
+  } else {
+    g.n_sub = n_sub_for(Cout);
+  }
+  if (!B.build(g, {term(0, Cin, kind, {wr})})) return DRS_E_INVALID;
+  m->gemms.push_back(std::move(g));
+  DRS_TRY(m->d_fblob.upload(m->fblob.data(), m->fblob.size() * sizeof(float)));
+  DRS_TRY(m->d_wblob.upload(m->wblob.data(), m->wblob.size()));
+  DRS_TRY(m->d_kblocks.upload(m->kb_all.data(), m->kb_all.size() * sizeof(KBlock)));
+  const int r = conv_gemm_set_smem_limits();
+  if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "cudaFuncSetAttribute(conv_gemm_kernel)");
+  return DRS_OK;
+}
+
+}  // namespace drs

@@ -1,0 +1,634 @@
+// DrsPlan: activation workspace, TMA descriptors, launch list, time tables, sampler, CUDA-graph replay.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+
+#include "engine.cuh"
+#include "small_kernels.cuh"
+
+namespace drs {
+
+// ------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 NHWC [B, H, W, C] seen as the 5-D tensor (c, x, py, y, b).
+//   plain view:    (C,  W,   1, H,   B)
+//   stride-2 view: (2C, W/2, 2, H/2, B) -- c = px * C + channel, so a 2x2 / 3x3 stride-2 tap is a plain box
+static int make_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, bool stride2, int ck, int tw,
+                    int th, int tb) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return DRS_E_CUDA;
+  }
+  const cuuint64_t e = 2;  // bytes per bf16
+  cuuint64_t dims[5], strides[4];
+  if (!stride2) {
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = B;
+    strides[0] = C * e;
+    strides[1] = static_cast<cuuint64_t>(W) * C * e;
+    strides[2] = static_cast<cuuint64_t>(W) * C * e;
+    strides[3] = static_cast<cuuint64_t>(H) * W * C * e;
+  } else {
+    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
+    strides[0] = 2 * C * e;
+    strides[1] = static_cast<cuuint64_t>(W) * C * e;
+    strides[2] = static_cast<cuuint64_t>(2) * W * C * e;
+    strides[3] = static_cast<cuuint64_t>(H) * W * C * e;
+  }
+  const cuuint32_t box[5] = {static_cast<cuuint32_t>(ck), static_cast<cuuint32_t>(tw), 1u,
+                             static_cast<cuuint32_t>(th), static_cast<cuuint32_t>(tb)};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw =
+      (ck == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : (ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] stride2=%d ck=%d box=(%d,%d,%d)", static_cast<int>(r),
+              B, H, W, C, static_cast<int>(stride2), ck, tw, th, tb);
+    return DRS_E_CUDA;
+  }
+  return DRS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan construction
+// ------------------------------------------------------------------------------------------------
+static void add_act(DrsPlan* p, size_t& cursor, const std::string& name, int C, int H, int W, bool fp32_map = false) {
+  ActTensor t;
+  t.name = name;
+  t.C = C;
+  t.H = H;
+  t.W = W;
+  t.fp32_map = fp32_map;
+  t.bytes = static_cast<size_t>(p->nb) * H * W * (fp32_map ? 4 : C * 2);
+  t.bytes = (t.bytes + 1023) & ~static_cast<size_t>(1023);
+  t.offset = cursor;
+  cursor += t.bytes;
+  p->acts[name] = t;
+}
+
+static void tile_geometry(int W, int H, int* tw, int* th, int* tb) {
+  int w = 16;
+  while (w > 1 && w / 2 >= W) w /= 2;  // smallest power of two >= W, capped at 16
+  int h = kTileM / w;
+  int hh = 1;
+  while (hh < H && hh < h) hh *= 2;     // smallest power of two >= H, capped at 128 / w
+  *tw = w;
+  *th = hh;
+  *tb = kTileM / (w * hh);
+}
+
+static int bind_launch(DrsPlan* p, int spec_idx, const void* src0, const void* src1, int gridW, int gridH, int srcH[2],
+                       int srcW[2], void* out, int OH, int OW, Launch* L) {
+  const DrsModel* m = p->m;
+  const GemmSpec& g = m->gemms[spec_idx];
+  memset(L, 0, sizeof(*L));
+  L->spec = spec_idx;
+  ConvArgs& a = L->args;
+  tile_geometry(gridW, gridH, &a.tw, &a.th, &a.tb);
+  a.W = gridW;
+  a.H = gridH;
+  a.B = p->nb;
+  a.tiles_x = (gridW + a.tw - 1) / a.tw;
+  a.tiles_y = (gridH + a.th - 1) / a.th;
+  const int tiles_b = (p->nb + a.tb - 1) / a.tb;
+  L->n_tiles = a.tiles_x * a.tiles_y * tiles_b;
+  const void* srcs[2] = {src0, src1};
+  CUtensorMap* maps[2] = {&L->map0, &L->map1};
+  for (int s = 0; s < g.n_src; ++s)
+    DRS_TRY(make_map(maps[s], srcs[s], p->nb, srcH[s], srcW[s], g.src_C[s], g.src_stride2[s] != 0, g.src_ck[s], a.tw,
+                     a.th, a.tb));
+  if (g.n_src == 1) L->map1 = L->map0;
+  a.kblocks = m->d_kblocks.as<KBlock>() + g.kb_dev_off;
+  a.wpack = m->d_wblob.as<uint8_t>();
+  a.nkb = g.nkb;
+  a.a_bytes = g.max_a_bytes;
+  a.stage_bytes = (g.max_a_bytes + g.max_b_bytes + 1023) & ~1023;
+  a.tmem_cols = g.tmem_cols;
+  a.n_sub = g.n_sub;
+  a.err = p->d_err;
+  // pipeline depth: as many CTAs per SM as TMEM allows (at most 3), each with up to 8 stages
+  int ctas = std::min(512 / g.tmem_cols, 3);
+  int stages = 2;
+  for (; ctas >= 1; --ctas) {
+    const int budget = (222 * 1024) / ctas - 8 * 1024;
+    stages = std::min({budget / a.stage_bytes, 8, g.nkb});
+    if (stages >= 3 || stages >= g.nkb || ctas == 1) break;
+  }
+  if (stages < 1) {
+    set_error("%s: stage of %d bytes does not fit shared memory", g.name.c_str(), a.stage_bytes);
+    return DRS_E_INVALID;
+  }
+  a.stages = stages;
+  L->smem = static_cast<size_t>(stages) * a.stage_bytes + 1024;
+  EpiArgs& e = a.epi;
+  e.out = out;
+  e.OH = OH;
+  e.OW = OW;
+  e.OC = g.OC;
+  e.oscale = g.oscale;
+  e.n_groups = g.n_groups;
+  e.group_n = g.n_sub;
+  e.col2 = g.col2;
+  e.flags = g.flags;
+  e.scale = m->f(g.scale);
+  e.bias = m->f(g.bias);
+  e.scale2 = m->f(g.scale2);
+  e.bias2 = m->f(g.bias2);
+  e.te = p->table.as<float>();
+  e.trow = p->d_trow;
+  e.te_stride = m->te_stride;
+  e.te_off = g.te_off;
+  e.pre_off = g.pre_off;
+  e.wvec = m->f(g.wvec);
+  e.bvec = m->f(g.bvec);
+  e.nvec = g.nvec;
+  return DRS_OK;
+}
+
+static int alloc_small(DrsPlan* p) {
+  const size_t n = static_cast<size_t>(p->nb);
+  DRS_TRY(p->small.alloc((3 * n + 16) * sizeof(int) + n * sizeof(float)));
+  DRS_CUDA(cudaMemset(p->small.p, 0, p->small.bytes));
+  int* base = p->small.as<int>();
+  p->d_trow = base;
+  p->d_uniq = base + n;
+  p->d_labels = base + 2 * n;
+  p->d_step = base + 3 * n;
+  p->d_err = base + 3 * n + 4;
+  p->d_tvals = reinterpret_cast<float*>(base + 3 * n + 16);
+  return DRS_OK;
+}
+
+int plan_create(DrsModel* m, int nb, int nx, int ncond, int S, int mag, DrsPlan** out) {
+  if (!m || !out) {
+    set_error("drs_plan_create: null argument");
+    return DRS_E_INVALID;
+  }
+  if (nb < 1 || nx < 1 || nb % nx || S < 16 || S % 8 || mag < 1) {
+    set_error("drs_plan_create: bad shape nb=%d nx=%d S=%d mag=%d (S must be a multiple of 8, >= 16)", nb, nx, S, mag);
+    return DRS_E_INVALID;
+  }
+  if (m->has_cond && ncond != 1 && ncond != nb) {
+    set_error("drs_plan_create: ncond must be 1 or nb");
+    return DRS_E_INVALID;
+  }
+  if (m->has_cond && m->desc.kind == DRS_MODEL_SUPERRES && S % mag) {
+    set_error("drs_plan_create: S=%d is not a multiple of the magnification %d", S, mag);
+    return DRS_E_INVALID;
+  }
+  DRS_CUDA(cudaSetDevice(m->device));
+  std::unique_ptr<DrsPlan> p(new DrsPlan());
+  p->m = m;
+  p->nb = nb;
+  p->nx = nx;
+  p->ncond = m->has_cond ? ncond : 0;
+  p->S = S;
+  p->mag = (m->desc.kind == DRS_MODEL_SUPERRES) ? mag : 1;
+  DRS_TRY(alloc_small(p.get()));
+
+  // activations (bf16 NHWC unless noted)
+  size_t cur = 0;
+  const int S1 = S, S2 = S / 2, S4 = S / 4, S8 = S / 8;
+  add_act(p.get(), cur, "h0", 16, S1, S1);
+  add_act(p.get(), cur, "b0.h", 32, S1, S1);
+  add_act(p.get(), cur, "b0.out", 32, S1, S1);
+  add_act(p.get(), cur, "d0", 32, S2, S2);
+  add_act(p.get(), cur, "b1.h", 64, S2, S2);
+  add_act(p.get(), cur, "b1.out", 64, S2, S2);
+  add_act(p.get(), cur, "d1", 64, S4, S4);
+  add_act(p.get(), cur, "b2.h", 128, S4, S4);
+  add_act(p.get(), cur, "b2.out", 128, S4, S4);
+  add_act(p.get(), cur, "d2", 128, S8, S8);
+  add_act(p.get(), cur, "bn.h", 256, S8, S8);
+  add_act(p.get(), cur, "bn.out", 256, S8, S8);
+  const int upC[4] = {256, 128, 64, 32};
+  const int upS[3] = {S8, S4, S2};
+  for (int i = 0; i < 3; ++i) {
+    const std::string si = std::to_string(i);
+    add_act(p.get(), cur, "g" + si, upC[i + 1], upS[i], upS[i]);
+    add_act(p.get(), cur, "psi" + si, 1, upS[i], upS[i], true);
+    add_act(p.get(), cur, "att" + si, upC[i + 1], 2 * upS[i], 2 * upS[i]);
+    add_act(p.get(), cur, "uc" + si, upC[i], upS[i], upS[i]);
+    add_act(p.get(), cur, "ut" + si, upC[i], 2 * upS[i], 2 * upS[i]);
+    if (i < 2) add_act(p.get(), cur, "x" + si, upC[i + 1], 2 * upS[i], 2 * upS[i]);
+  }
+  DRS_TRY(p->workspace.alloc(cur));
+  DRS_CUDA(cudaMemset(p->workspace.p, 0, cur));
+
+  // condition features: fp32 NHWC [ncond, S, S, 16] + scratch for the encoder (3 NCHW planes sets at LR and SR size)
+  if (m->has_cond) {
+    DRS_TRY(p->cond_feat.alloc(static_cast<size_t>(ncond) * S * S * 16 * sizeof(float)));
+    DRS_TRY(p->cond_tmp.alloc(static_cast<size_t>(ncond) * 4 * S * S * sizeof(float) * 3));
+  }
+  // a default one-row-per-sample time table so that drs_time_embed works without a sampler
+  DRS_TRY(p->table.alloc(static_cast<size_t>(nb) * m->te_stride * sizeof(float)));
+  p->table_rows = nb;
+
+  // launch list
+  uint8_t* ws = p->workspace.as<uint8_t>();
+  for (size_t gi = 0; gi < m->gemms.size(); ++gi) {
+    const GemmSpec& g = m->gemms[gi];
+    const ActTensor& s0 = p->acts.at(g.src_name[0]);
+    const void* src[2] = {ws + s0.offset, nullptr};
+    int sH[2] = {s0.H, 0}, sW[2] = {s0.W, 0};
+    if (g.n_src == 2) {
+      const ActTensor& s1 = p->acts.at(g.src_name[1]);
+      src[1] = ws + s1.offset;
+      sH[1] = s1.H;
+      sW[1] = s1.W;
+    }
+    const int gridH = g.src_stride2[0] ? s0.H / 2 : s0.H;
+    const int gridW = g.src_stride2[0] ? s0.W / 2 : s0.W;
+    if (g.n_src == 2) {
+      const int h1 = g.src_stride2[1] ? sH[1] / 2 : sH[1];
+      const int w1 = g.src_stride2[1] ? sW[1] / 2 : sW[1];
+      if (h1 != gridH || w1 != gridW) {
+        set_error("%s: source grids differ (%dx%d vs %dx%d)", g.name.c_str(), gridH, gridW, h1, w1);
+        return DRS_E_INVALID;
+      }
+    }
+    void* outp = nullptr;
+    int OH = gridH * g.oscale, OW = gridW * g.oscale;
+    if (!g.out_name.empty()) {
+      const ActTensor& o = p->acts.at(g.out_name);
+      outp = ws + o.offset;
+      if (o.H != OH || o.W != OW) {
+        set_error("%s: output grid mismatch", g.name.c_str());
+        return DRS_E_INVALID;
+      }
+    }
+    Launch L;
+    DRS_TRY(bind_launch(p.get(), static_cast<int>(gi), src[0], src[1], gridW, gridH, sH, sW, outp, OH, OW, &L));
+    if (g.flags & F_ROWSCALE) L.args.epi.psi = reinterpret_cast<const float*>(ws + p->acts.at(g.src_name[1]).offset);
+    p->launches.push_back(L);
+  }
+  *out = p.release();
+  return DRS_OK;
+}
+
+void plan_destroy(DrsPlan* p) {
+  if (!p) return;
+  if (p->graph_noise) cudaGraphExecDestroy(p->graph_noise);
+  if (p->graph_last) cudaGraphExecDestroy(p->graph_last);
+  delete p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// condition encoder (time-invariant)
+// ------------------------------------------------------------------------------------------------
+int cond_encode(DrsPlan* p, const float* cond, cudaStream_t st) {
+  const DrsModel* m = p->m;
+  if (!m->has_cond) return DRS_OK;
+  if (!cond) {
+    set_error("drs_cond_encode: null condition image");
+    return DRS_E_INVALID;
+  }
+  const int Cc = m->desc.cond_channels;
+  const int h = p->S / p->mag, w = h;
+  const int n = p->ncond;
+  const size_t plane = static_cast<size_t>(n) * Cc * p->S * p->S;  // big enough for LR and SR resolution
+  float* t0 = p->cond_tmp.as<float>();
+  float* t1 = t0 + plane;
+  float* t2 = t1 + plane;
+  auto conv = [&](const SmallConv& c, const float* in, const float* res, float* out, int H, int W, int relu,
+                  int nhwc) {
+    return launch_conv3x3_small(in, m->f(c.w), m->f(c.b), res, out, n, c.cin, c.cout, H, W, relu, nhwc, st);
+  };
+  // RRDB: three ResidualBlocks (conv-relu-conv + x), conv_out, + input   (UNet_model_superres.py:230-260)
+  const float* cur = cond;
+  float* bufs[2] = {t1, t2};
+  for (int i = 0; i < 3; ++i) {
+    DRS_CUDA(static_cast<cudaError_t>(conv(m->enc[2 * i], cur, nullptr, t0, h, w, 1, 0)));
+    float* o = bufs[i & 1];
+    DRS_CUDA(static_cast<cudaError_t>(conv(m->enc[2 * i + 1], t0, cur, o, h, w, 0, 0)));
+    cur = o;
+  }
+  DRS_CUDA(static_cast<cudaError_t>(conv(m->enc[6], cur, cond, t0, h, w, 0, 0)));  // t0 = encoded condition
+  const float* enc = t0;
+  if (m->desc.kind == DRS_MODEL_SUPERRES && p->mag > 1) {
+    DRS_CUDA(static_cast<cudaError_t>(launch_bicubic_up(t0, t1, n, Cc, h, w, p->mag, st)));
+    enc = t1;
+  }
+  DRS_CUDA(static_cast<cudaError_t>(conv(m->cond_conv, enc, nullptr, p->cond_feat.as<float>(), p->S, p->S, 0, 1)));
+  return DRS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// time tables: rows of [relu(mlp_i(enc)) for the 7 MLPs | 9-class border sums for the three UpConvBlocks]
+// ------------------------------------------------------------------------------------------------
+__global__ void border_class_kernel(const float* __restrict__ taps, float* __restrict__ table, int R, int C,
+                                    int te_stride, int pre_off) {
+  // taps: [R][9][C] per-tap sums  S_k[oc] = sum_ci W[oc,ci,k] * te[ci];  class (ry, rx): 0 = first, 1 = inner, 2 = last
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(R) * 9 * C;
+  if (idx >= total) return;
+  const int oc = static_cast<int>(idx % C);
+  const int cls = static_cast<int>((idx / C) % 9);
+  const int r = static_cast<int>(idx / (9LL * C));
+  const int ry = cls / 3, rx = cls % 3;
+  const float* t = taps + static_cast<size_t>(r) * 9 * C;
+  float acc = 0.f;
+  for (int ky = 0; ky < 3; ++ky) {
+    if ((ry == 0 && ky == 0) || (ry == 2 && ky == 2)) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      if ((rx == 0 && kx == 0) || (rx == 2 && kx == 2)) continue;
+      acc += t[(ky * 3 + kx) * C + oc];
+    }
+  }
+  table[static_cast<size_t>(r) * te_stride + pre_off + cls * C + oc] = acc;
+}
+
+// rows [r0, r0 + R) of the table from device arrays tvals[R] / labels[R]
+static int fill_table_rows(DrsPlan* p, float* table, const float* tvals, const int* labels, int R, cudaStream_t st) {
+  const DrsModel* m = p->m;
+  const size_t need = static_cast<size_t>(R) * (100 + 256 + 9 * 256) * sizeof(float);
+  if (p->scratch.bytes < need) {
+    DRS_CUDA(cudaStreamSynchronize(st));
+    DRS_TRY(p->scratch.alloc(need));
+  }
+  float* enc = p->scratch.as<float>();
+  float* hid = enc + static_cast<size_t>(R) * 100;
+  float* taps = hid + static_cast<size_t>(R) * 256;
+  DRS_CUDA(static_cast<cudaError_t>(
+      launch_pos_encoding(tvals, labels, m->f(m->label_emb), m->f(m->inv_freq), enc, R, st)));
+  for (int i = 0; i < 7; ++i) {
+    const TimeMlp& t = m->mlps[i];
+    DRS_CUDA(static_cast<cudaError_t>(
+        launch_sgemm_nt(enc, 100, m->f(t.w1), 100, m->f(t.b1), hid, t.C, R, t.C, 100, 1, st)));
+    DRS_CUDA(static_cast<cudaError_t>(
+        launch_sgemm_nt(hid, t.C, m->f(t.w2), t.C, m->f(t.b2), table + t.te_off, m->te_stride, R, t.C, t.C, 2, st)));
+    if (t.wtap >= 0) {
+      DRS_CUDA(static_cast<cudaError_t>(launch_sgemm_nt(table + t.te_off, m->te_stride, m->f(t.wtap), t.C, nullptr,
+                                                        taps, 9 * t.C, R, 9 * t.C, t.C, 0, st)));
+      const long long total = static_cast<long long>(R) * 9 * t.C;
+      border_class_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(taps, table, R, t.C,
+                                                                                      m->te_stride, t.pre_off);
+      DRS_CUDA(cudaGetLastError());
+    }
+  }
+  return DRS_OK;
+}
+
+static void rebind_table(DrsPlan* p) {
+  for (Launch& L : p->launches) L.args.epi.te = p->table.as<float>();
+}
+
+static void drop_graphs(DrsPlan* p) {
+  if (p->graph_noise) cudaGraphExecDestroy(p->graph_noise);
+  if (p->graph_last) cudaGraphExecDestroy(p->graph_last);
+  p->graph_noise = p->graph_last = nullptr;
+}
+
+__global__ void iota_rows_kernel(int* trow, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) trow[i] = i;
+}
+
+int time_embed(DrsPlan* p, const float* t_dev, const int* label_dev, cudaStream_t st) {
+  if (!t_dev) {
+    set_error("drs_time_embed: null timestep array");
+    return DRS_E_INVALID;
+  }
+  if (label_dev && p->m->label_emb < 0) {
+    set_error("drs_time_embed: labels given but the model has no label_emb");
+    return DRS_E_INVALID;
+  }
+  if (p->table_rows < p->nb) {
+    set_error("drs_time_embed: table too small");
+    return DRS_E_STATE;
+  }
+  DRS_TRY(fill_table_rows(p, p->table.as<float>(), t_dev, label_dev, p->nb, st));
+  iota_rows_kernel<<<1, 256, 0, st>>>(p->d_trow, p->nb);
+  DRS_CUDA(cudaGetLastError());
+  p->prepared = false;  // the table no longer holds the sampler's rows
+  return DRS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// UNet forward
+// ------------------------------------------------------------------------------------------------
+static int enqueue_forward(DrsPlan* p, const float* x, float* eps, cudaStream_t st) {
+  const DrsModel* m = p->m;
+  const ActTensor& h0 = p->acts.at("h0");
+  DRS_CUDA(static_cast<cudaError_t>(launch_conv0(x, m->f(m->conv0.w), m->f(m->conv0.b),
+                                                 m->has_cond ? p->cond_feat.as<float>() : nullptr,
+                                                 p->workspace.as<uint8_t>() + h0.offset, p->nb, p->nx,
+                                                 m->has_cond ? p->ncond : 1, m->desc.x_channels, p->S, st)));
+  for (Launch& L : p->launches) {
+    const GemmSpec& g = m->gemms[L.spec];
+    ConvArgs a = L.args;
+    if (g.epi_kind == EPI_OUT) a.epi.out = eps;
+    const int r = launch_conv_gemm(g.epi_kind, L.map0, L.map1, a, L.n_tiles, g.nsplit, L.smem, st);
+    if (r != 0) {
+      set_error("launch of %s failed: %s", g.name.c_str(), cudaGetErrorString(static_cast<cudaError_t>(r)));
+      return DRS_E_CUDA;
+    }
+  }
+  return DRS_OK;
+}
+
+int check_pipeline_error(DrsPlan* p, cudaStream_t st) {
+  int e = 0;
+  DRS_CUDA(cudaMemcpyAsync(&e, p->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaStreamSynchronize(st));
+  if (e != 0) {
+    set_error("tensor-core pipeline timed out (role %d: 1 = TMA producer, 2 = MMA issuer, 3 = epilogue)", e);
+    cudaMemsetAsync(p->d_err, 0, sizeof(int), st);
+    return DRS_E_PIPELINE;
+  }
+  return DRS_OK;
+}
+
+int unet_forward(DrsPlan* p, const float* x, float* eps, cudaStream_t st) {
+  if (!x || !eps) {
+    set_error("drs_unet_forward: null buffer");
+    return DRS_E_INVALID;
+  }
+  return enqueue_forward(p, x, eps, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampler
+// ------------------------------------------------------------------------------------------------
+int sampler_prepare(DrsPlan* p, int noise_steps, const float* c1, const float* c2, const float* c3,
+                    const int* labels_host, float cfg_scale, cudaStream_t st) {
+  const DrsModel* m = p->m;
+  if (noise_steps < 2 || !c1 || !c2 || !c3) {
+    set_error("drs_sampler_prepare: bad arguments");
+    return DRS_E_INVALID;
+  }
+  if (labels_host && m->label_emb < 0) {
+    set_error("drs_sampler_prepare: labels given but the model has no label_emb");
+    return DRS_E_INVALID;
+  }
+  // distinct labels -> table columns
+  std::vector<int> uniq, idx(p->nb, 0);
+  if (labels_host) {
+    for (int b = 0; b < p->nb; ++b) {
+      const int l = labels_host[b];
+      if (l < -1 || l >= m->desc.num_classes) {
+        set_error("drs_sampler_prepare: label %d out of range", l);
+        return DRS_E_INVALID;
+      }
+      auto it = std::find(uniq.begin(), uniq.end(), l);
+      if (it == uniq.end()) {
+        uniq.push_back(l);
+        idx[b] = static_cast<int>(uniq.size()) - 1;
+      } else {
+        idx[b] = static_cast<int>(it - uniq.begin());
+      }
+    }
+  } else {
+    uniq.push_back(-1);
+  }
+  p->n_uniq = static_cast<int>(uniq.size());
+  p->noise_steps = noise_steps;
+  p->cfg_scale = cfg_scale;
+  const int rows = noise_steps * p->n_uniq;
+  DRS_CUDA(cudaStreamSynchronize(st));
+  drop_graphs(p);
+  if (p->table_rows < rows) {
+    DRS_TRY(p->table.alloc(static_cast<size_t>(rows) * m->te_stride * sizeof(float)));
+    p->table_rows = rows;
+    rebind_table(p);
+  }
+  DevMem tv, lb;
+  std::vector<float> hc(static_cast<size_t>(noise_steps) * 4);
+  for (int i = 0; i < noise_steps; ++i) {
+    hc[4 * i + 0] = c1[i];
+    hc[4 * i + 1] = c2[i];
+    hc[4 * i + 2] = c3[i];
+    hc[4 * i + 3] = 0.f;
+  }
+  DRS_TRY(p->coef.upload(hc.data(), hc.size() * sizeof(float)));
+  p->d_coef = p->coef.as<float>();
+  DRS_CUDA(cudaMemcpy(p->d_uniq, idx.data(), p->nb * sizeof(int), cudaMemcpyHostToDevice));
+  // rows are ordered (step, distinct label); filled in chunks to bound the scratch
+  const int chunk = 4096;
+  DRS_TRY(tv.alloc(static_cast<size_t>(chunk) * sizeof(float)));
+  DRS_TRY(lb.alloc(static_cast<size_t>(chunk) * sizeof(int)));
+  std::vector<float> htv(chunk);
+  std::vector<int> hlb(chunk);
+  for (int r0 = 0; r0 < rows; r0 += chunk) {
+    const int R = std::min(chunk, rows - r0);
+    for (int r = 0; r < R; ++r) {
+      htv[r] = static_cast<float>((r0 + r) / p->n_uniq);
+      hlb[r] = uniq[(r0 + r) % p->n_uniq];
+    }
+    DRS_CUDA(cudaMemcpyAsync(tv.p, htv.data(), R * sizeof(float), cudaMemcpyHostToDevice, st));
+    DRS_CUDA(cudaMemcpyAsync(lb.p, hlb.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+    DRS_TRY(fill_table_rows(p, p->table.as<float>() + static_cast<size_t>(r0) * m->te_stride, tv.as<float>(),
+                            m->label_emb >= 0 ? lb.as<int>() : nullptr, R, st));
+    DRS_CUDA(cudaStreamSynchronize(st));
+  }
+  p->prepared = true;
+  p->begun = false;
+  return DRS_OK;
+}
+
+int sampler_begin(DrsPlan* p, float* x, float* noise, float* eps, int start_step, cudaStream_t st) {
+  if (!p->prepared) {
+    set_error("drs_sampler_begin: call drs_sampler_prepare first");
+    return DRS_E_STATE;
+  }
+  if (!x || !eps || start_step < 1 || start_step >= p->noise_steps) {
+    set_error("drs_sampler_begin: bad arguments (start_step=%d, noise_steps=%d)", start_step, p->noise_steps);
+    return DRS_E_INVALID;
+  }
+  if (x != p->x || noise != p->noise || eps != p->eps) drop_graphs(p);
+  p->x = x;
+  p->noise = noise;
+  p->eps = eps;
+  p->cur_step = start_step;
+  DRS_CUDA(static_cast<cudaError_t>(
+      launch_set_rows(p->d_trow, p->d_uniq, p->nb, p->d_step, start_step, p->n_uniq, st)));
+  p->begun = true;
+  return DRS_OK;
+}
+
+static int enqueue_step(DrsPlan* p, bool with_noise, cudaStream_t st) {
+  const DrsModel* m = p->m;
+  DRS_TRY(enqueue_forward(p, p->x, p->eps, st));
+  const size_t numel = static_cast<size_t>(p->nx) * m->desc.out_channels * p->S * p->S;
+  const int cfg = (p->nb == 2 * p->nx) ? 1 : 0;
+  DRS_CUDA(static_cast<cudaError_t>(launch_ddpm_update(p->x, p->eps, with_noise ? p->noise : nullptr, p->d_coef,
+                                                       p->d_step, numel, cfg, p->cfg_scale, st)));
+  DRS_CUDA(static_cast<cudaError_t>(launch_advance(p->d_trow, p->nb, p->n_uniq, p->d_step, st)));
+  return DRS_OK;
+}
+
+int sampler_step(DrsPlan* p, int use_graph, cudaStream_t st) {
+  if (!p->begun) {
+    set_error("drs_sampler_step: call drs_sampler_begin first");
+    return DRS_E_STATE;
+  }
+  if (p->cur_step < 1) {
+    set_error("drs_sampler_step: the sampler already reached step 0");
+    return DRS_E_STATE;
+  }
+  if (p->m->desc.x_channels != p->m->desc.out_channels) {
+    set_error("drs_sampler_step: x_channels != out_channels");
+    return DRS_E_INVALID;
+  }
+  // the reference injects noise for i > 1 and zeros at i == 1 (train_diffusion_superres.py:243-248)
+  const bool with_noise = (p->cur_step > 1) && p->noise != nullptr;
+  if (!use_graph) {
+    DRS_TRY(enqueue_step(p, with_noise, st));
+  } else {
+    cudaGraphExec_t& ge = with_noise ? p->graph_noise : p->graph_last;
+    if (!ge) {
+      cudaGraph_t graph = nullptr;
+      DRS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const int r = enqueue_step(p, with_noise, st);
+      const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (r != DRS_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return r;
+      }
+      DRS_CUDA(ce);
+      const cudaError_t ie = cudaGraphInstantiate(&ge, graph, 0);
+      cudaGraphDestroy(graph);
+      DRS_CUDA(ie);
+    }
+    DRS_CUDA(cudaGraphLaunch(ge, st));
+  }
+  p->cur_step -= 1;
+  return DRS_OK;
+}
+
+// drs_debug_conv2d: binds gemms[0] of a single-layer model to caller buffers and runs it once.
+int debug_bind_and_run(DrsPlan* p, const void* in, int gridW, int gridH, int srcH, int srcW, void* out, int OH, int OW,
+                       cudaStream_t st) {
+  int sH[2] = {srcH, 0}, sW[2] = {srcW, 0};
+  Launch L;
+  DRS_TRY(bind_launch(p, 0, in, nullptr, gridW, gridH, sH, sW, out, OH, OW, &L));
+  const GemmSpec& g = p->m->gemms[0];
+  const int r = launch_conv_gemm(g.epi_kind, L.map0, L.map1, L.args, L.n_tiles, g.nsplit, L.smem, st);
+  if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "launch_conv_gemm(debug)");
+  return DRS_OK;
+}
+
+int launches_per_step(const DrsPlan* p) { return static_cast<int>(p->launches.size()) + 3; }
+
+}  // namespace drs

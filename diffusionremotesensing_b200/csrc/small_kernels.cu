@@ -1,0 +1,463 @@
+// CUDA-core kernels around the tensor-core convolutions: condition encoder, conv0, time tables, DDPM update,
+// aggregation blend. Reference lines cited per kernel are in /root/reference (see DESIGN.md for the map).
+#include "small_kernels.cuh"
+
+#include <cuda_bf16.h>
+#include <math.h>
+
+namespace drs {
+
+static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// Tiny-channel 3x3 conv (RRDB condition encoder, UNet_model_superres.py:230-260,345,353)
+// ------------------------------------------------------------------------------------------------
+__global__ void conv3x3_small_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                     const float* __restrict__ bias, const float* __restrict__ residual,
+                                     float* __restrict__ out, int B, int Cin, int Cout, int H, int W, int relu,
+                                     int nhwc_out) {
+  __shared__ float sw[16 * 4 * 9];
+  __shared__ float sb[16];
+  for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const long long total = static_cast<long long>(B) * H * W;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = static_cast<int>(idx % W);
+  const int y = static_cast<int>((idx / W) % H);
+  const int b = static_cast<int>(idx / (static_cast<long long>(W) * H));
+  float acc[16];
+#pragma unroll
+  for (int co = 0; co < 16; ++co) acc[co] = (co < Cout) ? sb[co] : 0.f;
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float* ip = in + (static_cast<size_t>(b) * Cin + ci) * H * W;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const float v = __ldg(ip + static_cast<size_t>(yy) * W + xx);
+#pragma unroll
+        for (int co = 0; co < 16; ++co)
+          if (co < Cout) acc[co] = fmaf(v, sw[(co * Cin + ci) * 9 + ky * 3 + kx], acc[co]);
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 16; ++co) {
+    if (co >= Cout) break;
+    float v = acc[co];
+    if (relu) v = fmaxf(v, 0.f);
+    if (residual) v += residual[((static_cast<size_t>(b) * Cout + co) * H + y) * W + x];
+    if (nhwc_out)
+      out[((static_cast<size_t>(b) * H + y) * W + x) * Cout + co] = v;
+    else
+      out[((static_cast<size_t>(b) * Cout + co) * H + y) * W + x] = v;
+  }
+}
+
+int launch_conv3x3_small(const float* in, const float* w, const float* bias, const float* residual, float* out, int B,
+                         int Cin, int Cout, int H, int W, int relu, int nhwc_out, cudaStream_t s) {
+  if (Cin > 4 || Cout > 16) return static_cast<int>(cudaErrorInvalidValue);
+  const long long total = static_cast<long long>(B) * H * W;
+  conv3x3_small_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, w, bias, residual, out, B, Cin, Cout, H, W, relu,
+                                                        nhwc_out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bicubic x k upsample, ATen semantics (UNet_model_superres.py:348-351: F.interpolate(..., mode='bicubic'))
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+__device__ __forceinline__ void cubic_coeffs(float t, float* c) {
+  const float A = -0.75f;
+  c[0] = cubic2(t + 1.f, A);
+  c[1] = cubic1(t, A);
+  const float u = 1.f - t;
+  c[2] = cubic1(u, A);
+  c[3] = cubic2(u + 1.f, A);
+}
+
+__global__ void bicubic_up_kernel(const float* __restrict__ in, float* __restrict__ out, int BC, int H, int W, int OH,
+                                  int OW, float scale) {
+  const long long total = static_cast<long long>(BC) * OH * OW;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = static_cast<int>(idx % OW);
+  const int oy = static_cast<int>((idx / OW) % OH);
+  const int bc = static_cast<int>(idx / (static_cast<long long>(OW) * OH));
+  const float rx = scale * (ox + 0.5f) - 0.5f;
+  const float ry = scale * (oy + 0.5f) - 0.5f;
+  const float fx = floorf(rx), fy = floorf(ry);
+  const int ix = static_cast<int>(fx), iy = static_cast<int>(fy);
+  float cx[4], cy[4];
+  cubic_coeffs(rx - fx, cx);
+  cubic_coeffs(ry - fy, cy);
+  const float* ip = in + static_cast<size_t>(bc) * H * W;
+  float r = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int yy = min(max(iy - 1 + j, 0), H - 1);
+    float rowv = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int xx = min(max(ix - 1 + i, 0), W - 1);
+      rowv += __ldg(ip + static_cast<size_t>(yy) * W + xx) * cx[i];
+    }
+    r += rowv * cy[j];
+  }
+  out[idx] = r;
+}
+
+int launch_bicubic_up(const float* in, float* out, int B, int C, int H, int W, int k, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * C * H * k * W * k;
+  const float scale = static_cast<float>(1.0 / static_cast<double>(k));
+  bicubic_up_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, out, B * C, H, W, H * k, W * k, scale);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv0 + condition add -> bf16 NHWC (UNet_model_superres.py:342,355)
+// ------------------------------------------------------------------------------------------------
+__global__ void conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                             const float* __restrict__ cond, __nv_bfloat16* __restrict__ out, int nb, int nx,
+                             int ncond, int Cx, int S) {
+  __shared__ float sw[16 * 4 * 9];
+  __shared__ float sb[16];
+  for (int i = threadIdx.x; i < 16 * Cx * 9; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 16; i += blockDim.x) sb[i] = bias[i];
+  __syncthreads();
+  const long long total = static_cast<long long>(nb) * S * S;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % S);
+  const int py = static_cast<int>((idx / S) % S);
+  const int b = static_cast<int>(idx / (static_cast<long long>(S) * S));
+  float acc[16];
+#pragma unroll
+  for (int co = 0; co < 16; ++co) acc[co] = sb[co];
+  const int bx = b % nx;
+  for (int ci = 0; ci < Cx; ++ci) {
+    const float* ip = x + (static_cast<size_t>(bx) * Cx + ci) * S * S;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = py + ky - 1;
+      if (yy < 0 || yy >= S) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = px + kx - 1;
+        if (xx < 0 || xx >= S) continue;
+        const float v = __ldg(ip + static_cast<size_t>(yy) * S + xx);
+#pragma unroll
+        for (int co = 0; co < 16; ++co) acc[co] = fmaf(v, sw[(co * Cx + ci) * 9 + ky * 3 + kx], acc[co]);
+      }
+    }
+  }
+  if (cond) {
+    const float4* cp =
+        reinterpret_cast<const float4*>(cond + ((static_cast<size_t>(b % ncond) * S + py) * S + px) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 c4 = __ldg(cp + q);
+      acc[4 * q + 0] += c4.x;
+      acc[4 * q + 1] += c4.y;
+      acc[4 * q + 2] += c4.z;
+      acc[4 * q + 3] += c4.w;
+    }
+  }
+  uint32_t pk[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + static_cast<size_t>(idx) * 16);
+  o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
+int launch_conv0(const float* x, const float* w, const float* bias, const float* cond, void* out, int nb, int nx,
+                 int ncond, int Cx, int S, cudaStream_t s) {
+  if (Cx > 4) return static_cast<int>(cudaErrorInvalidValue);
+  const long long total = static_cast<long long>(nb) * S * S;
+  conv0_kernel<<<cdiv(total, 128), 128, 0, s>>>(x, w, bias, cond, reinterpret_cast<__nv_bfloat16*>(out), nb, nx,
+                                                ncond, Cx, S);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sinusoidal encoding [sin(t f_j) | cos(t f_j)], j < 50 (UNet_model_superres.py:328-335) + label embedding add
+// (generate_new_imgs/UNet_model_generation.py:300-301)
+// ------------------------------------------------------------------------------------------------
+__global__ void pos_encoding_kernel(const float* __restrict__ t, const int* __restrict__ label,
+                                    const float* __restrict__ emb, const float* __restrict__ inv_freq,
+                                    float* __restrict__ out, int R) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * 100) return;
+  const int r = idx / 100, j = idx % 100;
+  const float a = t[r] * inv_freq[j % 50];
+  float v = (j < 50) ? sinf(a) : cosf(a);
+  if (label && emb) {
+    const int l = label[r];
+    if (l >= 0) v += emb[l * 100 + j];
+  }
+  out[idx] = v;
+}
+
+int launch_pos_encoding(const float* t, const int* label, const float* emb, const float* inv_freq, float* out, int R,
+                        cudaStream_t s) {
+  pos_encoding_kernel<<<cdiv(static_cast<long long>(R) * 100, 256), 256, 0, s>>>(t, label, emb, inv_freq, out, R);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small fp32 GEMM for the time MLPs (Linear -> SiLU -> Linear -> ReLU, UNet_model_superres.py:143-151,161)
+// ------------------------------------------------------------------------------------------------
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
+__global__ void __launch_bounds__(256)
+sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K, int act) {
+  __shared__ float sA[SG_BK][SG_BM + 1];
+  __shared__ float sB[SG_BK][SG_BN + 1];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += SG_BK) {
+    for (int i = threadIdx.x; i < SG_BM * SG_BK; i += 256) {
+      const int r = i / SG_BK, k = i % SG_BK;
+      const int gm = m0 + r, gk = k0 + k;
+      sA[k][r] = (gm < M && gk < K) ? A[static_cast<size_t>(gm) * lda + gk] : 0.f;
+      const int gn = n0 + r;
+      sB[k][r] = (gn < N && gk < K) ? B[static_cast<size_t>(gn) * ldb + gk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j] + (bias ? bias[gn] : 0.f);
+      if (act == 1) v = v / (1.f + expf(-v));
+      if (act == 2) v = fmaxf(v, 0.f);
+      C[static_cast<size_t>(gm) * ldc + gn] = v;
+    }
+  }
+}
+
+int launch_sgemm_nt(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M,
+                    int N, int K, int act, cudaStream_t s) {
+  dim3 grid(cdiv(N, SG_BN), cdiv(M, SG_BM));
+  sgemm_nt_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, act);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// DDPM posterior update (train_diffusion_superres.py:240-249) and CFG lerp
+// (generate_new_imgs/train_diffusion_generation.py:239-242)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ddpm_one(float x, float eps, float z, float c1, float c2, float c3, bool has_z) {
+  // 1/sqrt(a) * (x - ((1-a)/sqrt(1-ah)) * eps) + sqrt(b) * z  -- each op rounded like the reference (no FMA)
+  float r = __fmul_rn(c1, __fsub_rn(x, __fmul_rn(c2, eps)));
+  if (has_z) r = __fadd_rn(r, __fmul_rn(c3, z));
+  return r;
+}
+__device__ __forceinline__ float lerp_aten(float u, float c, float w) {
+  // at::lerp(start=u, end=c, weight=w): w < 0.5 ? u + w*(c-u) : c - (c-u)*(1-w)
+  const float d = __fsub_rn(c, u);
+  return (fabsf(w) < 0.5f) ? __fadd_rn(u, __fmul_rn(w, d)) : __fsub_rn(c, __fmul_rn(d, __fsub_rn(1.f, w)));
+}
+
+__global__ void ddpm_update_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                                   const float* __restrict__ noise, const float* __restrict__ coef,
+                                   const int* __restrict__ step, size_t n4, int cfg, float cfg_scale) {
+  const float4 cf = __ldg(reinterpret_cast<const float4*>(coef) + __ldg(step));
+  const bool has_z = (noise != nullptr) && (cf.z != 0.f || true);
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 xv = reinterpret_cast<float4*>(x)[i];
+    float4 ev = __ldg(reinterpret_cast<const float4*>(eps) + i);
+    if (cfg) {
+      const float4 uv = __ldg(reinterpret_cast<const float4*>(eps) + n4 + i);
+      ev.x = lerp_aten(uv.x, ev.x, cfg_scale);
+      ev.y = lerp_aten(uv.y, ev.y, cfg_scale);
+      ev.z = lerp_aten(uv.z, ev.z, cfg_scale);
+      ev.w = lerp_aten(uv.w, ev.w, cfg_scale);
+    }
+    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_z) zv = __ldg(reinterpret_cast<const float4*>(noise) + i);
+    xv.x = ddpm_one(xv.x, ev.x, zv.x, cf.x, cf.y, cf.z, has_z);
+    xv.y = ddpm_one(xv.y, ev.y, zv.y, cf.x, cf.y, cf.z, has_z);
+    xv.z = ddpm_one(xv.z, ev.z, zv.z, cf.x, cf.y, cf.z, has_z);
+    xv.w = ddpm_one(xv.w, ev.w, zv.w, cf.x, cf.y, cf.z, has_z);
+    reinterpret_cast<float4*>(x)[i] = xv;
+  }
+}
+
+int launch_ddpm_update(float* x, const float* eps, const float* noise, const float* coef, const int* step,
+                       size_t numel, int cfg, float cfg_scale, cudaStream_t s) {
+  if (numel % 4) return static_cast<int>(cudaErrorInvalidValue);
+  const size_t n4 = numel / 4;
+  int blocks = cdiv(static_cast<long long>(n4), 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ddpm_update_kernel<<<blocks, 256, 0, s>>>(x, eps, noise, coef, step, n4, cfg, cfg_scale);
+  return static_cast<int>(cudaGetLastError());
+}
+
+__global__ void advance_kernel(int* trow, int n, int dec, int* step) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) trow[i] -= dec;
+  if (threadIdx.x == 0) *step -= 1;
+}
+int launch_advance(int* trow, int n, int dec, int* step, cudaStream_t s) {
+  advance_kernel<<<1, 256, 0, s>>>(trow, n, dec, step);
+  return static_cast<int>(cudaGetLastError());
+}
+__global__ void set_rows_kernel(int* trow, const int* uniq, int n, int* step, int step_value, int mul) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) trow[i] = step_value * mul + (uniq ? uniq[i] : 0);
+  if (threadIdx.x == 0) *step = step_value;
+}
+int launch_set_rows(int* trow, const int* uniq, int n, int* step, int step_value, int mul, cudaStream_t s) {
+  set_rows_kernel<<<1, 256, 0, s>>>(trow, uniq, n, step, step_value, mul);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Aggregation blend (Aggregation_Sampling.py:91-110)
+// ------------------------------------------------------------------------------------------------
+__global__ void blend_gather_kernel(const float* __restrict__ patches, const int* __restrict__ ys, int ny,
+                                    const int* __restrict__ xs, int nx, const float* __restrict__ weight,
+                                    float* __restrict__ out, float* __restrict__ wsum_out, int C, int H, int W,
+                                    int P, int do_clamp) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y;
+  if (X >= W) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float cnt = 0.f;
+  const size_t pp = static_cast<size_t>(P) * P;
+  for (int iy = 0; iy < ny; ++iy) {
+    const int ly = Y - __ldg(ys + iy);
+    if (ly < 0 || ly >= P) continue;
+    for (int ix = 0; ix < nx; ++ix) {
+      const int lx = X - __ldg(xs + ix);
+      if (lx < 0 || lx >= P) continue;
+      const float w = __ldg(weight + static_cast<size_t>(ly) * P + lx);
+      const float* pb = patches + static_cast<size_t>(iy * nx + ix) * C * pp + static_cast<size_t>(ly) * P + lx;
+      for (int c = 0; c < C; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(__ldg(pb + c * pp), w));
+      cnt = __fadd_rn(cnt, w);
+    }
+  }
+  for (int c = 0; c < C; ++c) {
+    float v = __fdiv_rn(acc[c], cnt);
+    if (do_clamp) v = fminf(fmaxf(v, 0.f), 1.f);
+    out[(static_cast<size_t>(c) * H + Y) * W + X] = v;
+  }
+  if (wsum_out) wsum_out[static_cast<size_t>(Y) * W + X] = cnt;
+}
+
+int launch_blend_gather(const float* patches, const int* ys, int ny, const int* xs, int nx, const float* weight,
+                        float* out, float* wsum_out, int C, int H, int W, int P, int do_clamp, cudaStream_t s) {
+  if (C > 4) return static_cast<int>(cudaErrorInvalidValue);
+  dim3 grid(cdiv(W, 256), H);
+  blend_gather_kernel<<<grid, 256, 0, s>>>(patches, ys, ny, xs, nx, weight, out, wsum_out, C, H, W, P, do_clamp);
+  return static_cast<int>(cudaGetLastError());
+}
+
+__global__ void blend_accumulate_kernel(const float* __restrict__ patch, const float* __restrict__ weight,
+                                        float* __restrict__ acc, float* __restrict__ wsum, int C, int H, int W, int P,
+                                        int y0, int x0) {
+  const int lx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ly = blockIdx.y;
+  if (lx >= P) return;
+  const float w = weight[static_cast<size_t>(ly) * P + lx];
+  const size_t o = static_cast<size_t>(y0 + ly) * W + (x0 + lx);
+  for (int c = 0; c < C; ++c) {
+    const size_t oi = static_cast<size_t>(c) * H * W + o;
+    acc[oi] = __fadd_rn(acc[oi], __fmul_rn(patch[(static_cast<size_t>(c) * P + ly) * P + lx], w));
+  }
+  wsum[o] = __fadd_rn(wsum[o], w);
+}
+int launch_blend_accumulate(const float* patch, const float* weight, float* acc, float* wsum, int C, int H, int W,
+                            int P, int y0, int x0, cudaStream_t s) {
+  dim3 grid(cdiv(P, 128), P);
+  blend_accumulate_kernel<<<grid, 128, 0, s>>>(patch, weight, acc, wsum, C, H, W, P, y0, x0);
+  return static_cast<int>(cudaGetLastError());
+}
+__global__ void blend_finalize_kernel(float* __restrict__ acc, const float* __restrict__ wsum, int C, size_t HW,
+                                      int do_clamp, int* zero_flag) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  const float w = wsum[i];
+  if (w == 0.f && zero_flag) atomicExch(zero_flag, 1);
+  for (int c = 0; c < C; ++c) {
+    float v = __fdiv_rn(acc[c * HW + i], w);
+    if (do_clamp) v = fminf(fmaxf(v, 0.f), 1.f);
+    acc[c * HW + i] = v;
+  }
+}
+int launch_blend_finalize(float* acc, const float* wsum, int C, int H, int W, int do_clamp, int* zero_flag,
+                          cudaStream_t s) {
+  const size_t HW = static_cast<size_t>(H) * W;
+  blend_finalize_kernel<<<cdiv(static_cast<long long>(HW), 256), 256, 0, s>>>(acc, wsum, C, HW, do_clamp, zero_flag);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout converters (layer-level debug entry points only)
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int C,
+                                         int H, int W) {
+  const long long total = static_cast<long long>(B) * C * H * W;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C);
+  const long long p = idx / C;
+  const int x = static_cast<int>(p % W);
+  const int y = static_cast<int>((p / W) % H);
+  const int b = static_cast<int>(p / (static_cast<long long>(W) * H));
+  out[idx] = __float2bfloat16_rn(in[((static_cast<size_t>(b) * C + c) * H + y) * W + x]);
+}
+__global__ void nhwc_bf16_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int B, int C,
+                                         int H, int W) {
+  const long long total = static_cast<long long>(B) * C * H * W;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = static_cast<int>(idx % W);
+  const int y = static_cast<int>((idx / W) % H);
+  const int c = static_cast<int>((idx / (static_cast<long long>(W) * H)) % C);
+  const int b = static_cast<int>(idx / (static_cast<long long>(W) * H * C));
+  out[idx] = __bfloat162float(in[((static_cast<size_t>(b) * H + y) * W + x) * C + c]);
+}
+int launch_nchw_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * C * H * W;
+  nchw_to_nhwc_bf16_kernel<<<cdiv(total, 256), 256, 0, s>>>(in, reinterpret_cast<__nv_bfloat16*>(out), B, C, H, W);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_nhwc_bf16_to_nchw(const void* in, float* out, int B, int C, int H, int W, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * C * H * W;
+  nhwc_bf16_to_nchw_kernel<<<cdiv(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, B, C, H,
+                                                            W);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace drs
