@@ -1,0 +1,167 @@
+"""Drop-in ``split_aggregation_sampling`` (Aggregation_Sampling.py:9-138) on the CUDA path.
+
+Same constructor, public attributes (``patches_lr``, ``patches_sr_infos``, ``weight``) and methods (``patchifier``,
+``aggregation_sampling``, ``gaussian_weights``). Differences in HOW, not WHAT:
+
+  * the reference super-resolves the patches one after another with ``sample(1, ...)``; here they run as batches
+    through ``Diffusion.sample_batched`` (every patch is an independent chain, eval-mode BatchNorm has no
+    cross-sample statistics);
+  * with ``torch.distributed`` initialised the row-major patch list is block-partitioned over the ranks, each rank
+    samples its block on its own GPU, one gather brings the finished patches to rank 0, which blends them in the
+    reference's patch order (so the blend is bit-identical whatever the world size) and broadcasts the scene;
+  * the Gaussian overlap blend, the division and the clamp are one CUDA kernel (``drs_blend``) that accumulates
+    each output pixel in patch order with separately rounded fp32 multiply and add, like the reference's
+    ``im_res[...] += patch_sr * weight`` sequence.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from numpy import exp, pi, sqrt
+
+from . import _native as N
+
+
+def partition_blocks(n_items: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous block partition of range(n_items): the first n_items % world_size ranks get one extra item."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    base, extra = divmod(n_items, world_size)
+    out, start = [], 0
+    for r in range(world_size):
+        size = base + (1 if r < extra else 0)
+        out.append((start, start + size))
+        start += size
+    return out
+
+
+def gather_blocks(local: torch.Tensor, counts: Sequence[int], dst: int = 0, group=None) -> Optional[torch.Tensor]:
+    """Gathers per-rank blocks [counts[r], ...] to rank `dst` in rank order (the one collective of the path)."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    cap = max(counts)
+    padded = local
+    if local.shape[0] != cap:
+        padded = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]] = local
+    padded = padded.contiguous()
+    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+def blend_patches(patches: torch.Tensor, infos: Sequence[Tuple[int, int, int, int]], weight2d: torch.Tensor,
+                  height: int, width: int, clamp: bool = True):
+    """drs_blend on device tensors: patches [n, C, P, P] fp32, weight2d [P, P] fp32 -> ([1, C, H, W], [H, W])."""
+    dev = patches.device
+    if dev.type != "cuda":
+        raise RuntimeError("drs_blend runs on a CUDA device only; there is no CPU fallback")
+    n, ch, P, _ = patches.shape
+    coords = torch.tensor([list(i) for i in infos], dtype=torch.int32).contiguous()
+    out = torch.empty((1, ch, height, width), device=dev, dtype=torch.float32)
+    wsum = torch.empty((height, width), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        N.check(N.lib().drs_blend(N.ptr(patches.contiguous()), N.ptr(coords), n, N.ptr(weight2d.contiguous()),
+                                  N.ptr(out), N.ptr(wsum), ch, height, width, P, 1 if clamp else 0,
+                                  N.stream_ptr(dev)))
+    return out, wsum
+
+
+class split_aggregation_sampling:
+    def __init__(self, img_lr, patch_size, stride, magnification_factor, diffusion_model, device, patch_batch=32):
+        assert stride <= patch_size
+        self.img_lr = img_lr
+        self.patch_size = patch_size
+        self.stride = stride
+        self.magnification_factor = magnification_factor
+        self.diffusion_model = diffusion_model
+        self.device = device
+        self.model = diffusion_model.model
+        self.patch_batch = patch_batch
+        batch_size, channels, height, width = img_lr.shape
+        if height < patch_size or width < patch_size:
+            raise ValueError("the image (%d x %d) is smaller than one patch (%d)" % (height, width, patch_size))
+        self.patches_lr, self.patches_sr_infos = self.patchifier(img_lr, patch_size, stride, magnification_factor)
+        self.weight = self.gaussian_weights(patch_size * magnification_factor, patch_size * magnification_factor,
+                                            batch_size)
+
+    def patchifier(self, img_to_split, patch_size, stride=None, magnification_factor=1):
+        """Row-major windows with the last row / column clamped to the border and duplicates dropped
+        (Aggregation_Sampling.py:30-74). Returns views of the image and the SR-space (y0, y1, x0, x1) tuples."""
+        stride = patch_size if stride is None else stride
+        _, _, height, width = img_to_split.shape
+        k = magnification_factor
+        starts_y = [min(y, height - patch_size) for y in range(0, height + 1, stride)]
+        starts_x = [min(x, width - patch_size) for x in range(0, width + 1, stride)]
+        patches_lr, infos, seen = [], [], set()
+        for ys in starts_y:
+            for xs in starts_x:
+                info = (ys * k, (ys + patch_size) * k, xs * k, (xs + patch_size) * k)
+                if info in seen:
+                    continue
+                seen.add(info)
+                patches_lr.append(img_to_split[:, :, ys:ys + patch_size, xs:xs + patch_size])
+                infos.append(info)
+        return patches_lr, infos
+
+    def gaussian_weights(self, tile_width, tile_height, nbatches):
+        """float64 outer product of two Gaussians (x midpoint (W-1)/2, y midpoint H/2, variance 0.01 of the
+        normalised coordinate), cast to fp32 and tiled to [nbatches, 3, H, W] (Aggregation_Sampling.py:118-138).
+        Evaluated with numpy scalars on the host exactly like the reference; never recomputed on the device."""
+        var = 0.01
+        mid_x = (tile_width - 1) / 2
+        mid_y = tile_height / 2
+        norm = sqrt(2 * pi * var)
+        x_probs = [exp(-(x - mid_x) * (x - mid_x) / (tile_width * tile_width) / (2 * var)) / norm
+                   for x in range(tile_width)]
+        y_probs = [exp(-(y - mid_y) * (y - mid_y) / (tile_height * tile_height) / (2 * var)) / norm
+                   for y in range(tile_height)]
+        weights = torch.tensor(np.outer(y_probs, x_probs)).to(torch.float32).to(self.device)
+        return torch.tile(weights, (nbatches, 3, 1, 1))
+
+    # -- sampling ------------------------------------------------------------------------------------------------
+    def sample_patches(self, indices: Sequence[int], noise: Optional[Callable] = None,
+                       x_T: Optional[Callable] = None) -> torch.Tensor:
+        """SR patches [len(indices), C, P*k, P*k] for the given patch indices, in batches of `patch_batch`.
+        noise(patch_index, step) / x_T(patch_index) inject per-patch noise (parity tests)."""
+        outs = []
+        dm = self.diffusion_model
+        for b0 in range(0, len(indices), self.patch_batch):
+            idx = list(indices[b0:b0 + self.patch_batch])
+            lr = torch.cat([self.patches_lr[i] for i in idx], dim=0).to(self.device)
+            xt = None if x_T is None else torch.cat([x_T(i) for i in idx], dim=0)
+            nz = None if noise is None else (lambda step, idx=idx: torch.cat([noise(i, step) for i in idx], dim=0))
+            outs.append(dm.sample_batched(self.model, lr, input_channels=lr.shape[1], x_T=xt, noise=nz))
+        return torch.cat(outs, dim=0)
+
+    def aggregation_sampling(self, noise: Optional[Callable] = None, x_T: Optional[Callable] = None, group=None):
+        batch_size, channels, height, width = self.img_lr.shape
+        if batch_size != 1:
+            raise ValueError("aggregation sampling handles one scene at a time (batch size 1), like the reference")
+        k = self.magnification_factor
+        n = len(self.patches_lr)
+        import torch.distributed as dist
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if distributed:
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+            blocks = partition_blocks(n, world)
+            lo, hi = blocks[rank]
+            local = self.sample_patches(range(lo, hi), noise, x_T)
+            patches = gather_blocks(local, [b - a for a, b in blocks], dst=0, group=group)
+        else:
+            rank = 0
+            patches = self.sample_patches(range(n), noise, x_T)
+        H, W = height * k, width * k
+        if rank == 0:
+            im_res, _ = blend_patches(patches, self.patches_sr_infos, self.weight[0, 0], H, W, clamp=True)
+        else:
+            im_res = torch.empty((1, channels, H, W), device=self.device, dtype=torch.float32)
+        if distributed:
+            dist.broadcast(im_res, src=0, group=group)
+        return im_res

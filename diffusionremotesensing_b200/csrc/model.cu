@@ -268,6 +268,11 @@ static ConvTerm term(int src, int C, int kind, std::vector<WeightRef> stack, int
 static int n_sub_for(int OC) { return OC > 128 ? 128 : OC; }
 
 // ResConvBlock (UNet_model_superres.py:110-172) as two launches.
+static const char* skip_conv_name(int kind) {
+  // ResConvBlock's skip conv: UNet_model_superres.py:129, UNet_model_SAR_TO_NDVI.py:126, UNet_model_generation.py:127
+  return kind == DRS_MODEL_SUPERRES ? ".conv_upsampled_lr_img" : (kind == DRS_MODEL_SAR_TO_NDVI ? ".conv_SAR_img" : ".conv_skip");
+}
+
 static bool build_res_block(Builder& B, const std::string& p, int cin, int cout, bool has_skip, const std::string& in,
                             const std::string& mid, const std::string& out, int te_off) {
   DrsModel* m = B.m;
@@ -290,8 +295,8 @@ static bool build_res_block(Builder& B, const std::string& p, int cin, int cout,
     g.bias = B.push(b);
     std::vector<WeightRef> stack{wref(w1, cout, cin)};
     if (has_skip) {
-      const auto* ws = B.get(p + ".conv_upsampled_lr_img.weight", static_cast<size_t>(cout) * cin * 9);
-      const auto* bs = B.get(p + ".conv_upsampled_lr_img.bias", cout);
+      const auto* ws = B.get(p + skip_conv_name(m->desc.kind) + ".weight", static_cast<size_t>(cout) * cin * 9);
+      const auto* bs = B.get(p + skip_conv_name(m->desc.kind) + ".bias", cout);
       if (!ws || !bs) return false;
       stack.push_back(wref(ws, cout, cin));
       g.flags |= F_DUAL_POST;

@@ -50,7 +50,7 @@ class ResConvBlock(nn.Module):
     """Residual block parameters (UNet_model_superres.py:110-151). The BatchNorm modules are registered both as
     attributes and inside the Sequentials, so both key families appear in the state_dict like in the reference."""
 
-    def __init__(self, in_ch, out_ch, time_emb_dim, device):
+    def __init__(self, in_ch, out_ch, time_emb_dim, device, skip_name="conv_upsampled_lr_img"):
         super().__init__()
         self.time_mlp = _time_mlp(out_ch, device)
         self.batch_norm1 = nn.BatchNorm2d(out_ch, device=device)
@@ -59,7 +59,8 @@ class ResConvBlock(nn.Module):
         self.relu = nn.ReLU(inplace=False)
         self.conv1 = nn.Sequential(nn.Conv2d(in_ch, out_ch, 3, padding="same", device=device), self.batch_norm1,
                                    self.relu)
-        self.conv_upsampled_lr_img = nn.Conv2d(in_ch, out_ch, 3, padding=1)
+        # the skip conv is called conv_upsampled_lr_img / conv_SAR_img / conv_skip in the three reference files
+        setattr(self, skip_name, nn.Conv2d(in_ch, out_ch, 3, padding=1))
         self.conv2 = nn.Sequential(nn.Conv2d(out_ch, out_ch, 3, padding="same", device=device), self.batch_norm2)
         self.shortcut_conv = nn.Sequential(nn.Conv2d(in_ch, out_ch, 1, padding="same", device=device),
                                            self.shortcut_batch_norm)
@@ -142,14 +143,15 @@ class _NativeUNet(nn.Module):
     """Shared trunk + the bridge to the C ABI."""
 
     _kind = N.MODEL_SUPERRES
+    _skip_name = "conv_upsampled_lr_img"
 
     def _build_trunk(self, device):
         dc, uc = DOWN_CHANNELS, UP_CHANNELS
-        self.conv_blocks = nn.ModuleList([ResConvBlock(dc[i], dc[i + 1], TIME_EMB_DIM, device)
+        self.conv_blocks = nn.ModuleList([ResConvBlock(dc[i], dc[i + 1], TIME_EMB_DIM, device, self._skip_name)
                                           for i in range(len(dc) - 2)])
         self.downs = nn.ModuleList([nn.Conv2d(dc[i + 1], dc[i + 1], 3, stride=2, padding=1, device=device)
                                     for i in range(len(dc) - 2)])
-        self.bottle_neck = ResConvBlock(dc[-2], dc[-1], TIME_EMB_DIM, device)
+        self.bottle_neck = ResConvBlock(dc[-2], dc[-1], TIME_EMB_DIM, device, self._skip_name)
         self.gating_signals = nn.ModuleList([gating_signal(uc[i], uc[i + 1], device) for i in range(len(uc) - 2)])
         self.attention_blocks = nn.ModuleList([AttentionBlock(uc[i + 1], uc[i + 1], uc[i + 1], device)
                                                for i in range(len(uc) - 2)])
@@ -310,6 +312,7 @@ class Residual_Attention_UNet_superres(_NativeUNet):
 
 class Residual_Attention_UNet_SAR_TO_NDVI(_NativeUNet):
     _kind = N.MODEL_SAR_TO_NDVI
+    _skip_name = "conv_SAR_img"
 
     def __init__(self, SAR_channels=2, NDVI_channels=1, device=None):
         super().__init__()
@@ -339,6 +342,7 @@ class Residual_Attention_UNet_SAR_TO_NDVI(_NativeUNet):
 
 class Residual_Attention_UNet_generation(_NativeUNet):
     _kind = N.MODEL_GENERATION
+    _skip_name = "conv_skip"
 
     def __init__(self, image_channels=3, out_dim=3, num_classes=None, device=None):
         super().__init__()
