@@ -167,6 +167,7 @@ struct DrsPlan {
   float* eps = nullptr;
   bool prepared = false, begun = false;
   cudaGraphExec_t graph_noise = nullptr, graph_last = nullptr;
+  cudaStream_t capture_stream = nullptr;
   const float* last_x = nullptr;
   float* last_eps = nullptr;
 };

@@ -292,6 +292,7 @@ void plan_destroy(DrsPlan* p) {
   if (!p) return;
   if (p->graph_noise) cudaGraphExecDestroy(p->graph_noise);
   if (p->graph_last) cudaGraphExecDestroy(p->graph_last);
+  if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
   delete p;
 }
 
@@ -598,10 +599,13 @@ int sampler_step(DrsPlan* p, int use_graph, cudaStream_t st) {
   } else {
     cudaGraphExec_t& ge = with_noise ? p->graph_noise : p->graph_last;
     if (!ge) {
+      // Capture on a private stream: the caller's stream may be the legacy default stream, which cannot be
+      // captured. Nothing executes during capture; the instantiated graph is replayed on the caller's stream.
+      if (!p->capture_stream) DRS_CUDA(cudaStreamCreateWithFlags(&p->capture_stream, cudaStreamNonBlocking));
       cudaGraph_t graph = nullptr;
-      DRS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      const int r = enqueue_step(p, with_noise, st);
-      const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      DRS_CUDA(cudaStreamBeginCapture(p->capture_stream, cudaStreamCaptureModeThreadLocal));
+      const int r = enqueue_step(p, with_noise, p->capture_stream);
+      const cudaError_t ce = cudaStreamEndCapture(p->capture_stream, &graph);
       if (r != DRS_OK) {
         if (graph) cudaGraphDestroy(graph);
         return r;

@@ -1,5 +1,5 @@
 // CUDA-core kernels around the tensor-core convolutions: condition encoder, conv0, time tables, DDPM update,
-// aggregation blend. Reference lines cited per kernel are in /root/reference (see DESIGN.md for the map).
+// aggregation blend. Reference lines cited per kernel are relative to the reference checkout (see DESIGN.md for the map).
 #include "small_kernels.cuh"
 
 #include <cuda_bf16.h>

@@ -61,6 +61,22 @@ def synthetic_state_dict(model: torch.nn.Module, seed: int) -> dict:
     return {k: v.detach().clone() for k, v in model.state_dict().items()}
 
 
+def default_init_model(family: str, seed: int = 0, bn_seed: int = 1):
+    """SURVEY.md section 8d synthetic weights: the constructor's default initialisation under torch.manual_seed(seed),
+    then BatchNorm weight ~ U(0.5, 1.5), bias ~ N(0, 0.1), running_mean ~ N(0, 0.1), running_var ~ U(0.5, 1.5)."""
+    torch.manual_seed(seed)
+    m = build_model(family)
+    g = torch.Generator().manual_seed(bn_seed)
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.uniform_(0.5, 1.5, generator=g)
+                mod.bias.normal_(0.0, 0.1, generator=g)
+                mod.running_mean.normal_(0.0, 0.1, generator=g)
+                mod.running_var.uniform_(0.5, 1.5, generator=g)
+    return m, {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
 def np_randn(seed, *shape) -> torch.Tensor:
     rng = np.random.Generator(np.random.PCG64(seed))
     return torch.from_numpy(rng.standard_normal(size=shape).astype(np.float32))
