@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the reverse-diffusion sampling hot path (BASELINE.json metric, config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (N = 1): super-resolution x2, LR 128 -> 256, batch n = 16 stochastic samples of one LR image, 1500-step cosine
+schedule, synthetic Sentinel-2-shaped RGB input, random-init weights (reference default init under manual_seed(0) +
+randomised BatchNorm statistics). A "step" is one reverse step of the whole batch: one UNet
+evaluation + the DDPM posterior update with freshly drawn noise. With N > 1 every rank runs the same per-GPU batch on
+its own GPU (weak scaling, no data-path collective).
+
+  value      image-steps per second over all GPUs with x_t, the condition features and the time tables resident in HBM
+  e2e        the same metric through the public API, Diffusion.sample(n, model, lr_img) with noise_steps = K + 1,
+             from pinned host tensors to a host result: H2D of lr_img and x_T, condition encode, time-table
+             preparation, K graph-replayed steps, D2H of the samples -- all inside the timed region
+  roofline   tensor-core bound: algorithmic conv FLOPs of one UNet evaluation / summed CUDA-event time of the
+             tcgen05 implicit-GEMM launches (drs_plan_profile), against MEASURED_PEAKS.json bf16_tflops_sustained
+  cpu_baseline  the reference algorithm (oracle port: the same torch CPU ops the reference's modules call) timed on
+             this box's host cores on a bounded sample of the same workload
+
+--impl reference prints the CPU arm alone (rank 0 only under torchrun).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "unet_denoise_image_steps_per_sec"
+UNIT = "image-steps/s"
+NOISE_STEPS = 1500
+BATCH = 16
+S = 256
+MAG = 2
+WORKLOAD = "superres_x2_LR128to256_batch16_cosine1500"
+
+
+def rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tflops": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops"))), "hbm_gbs": float(p["hbm_gbs"]),
+                "source": "MEASURED_PEAKS.json bf16_tflops_sustained"}
+    return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md, sustained)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.proc = None
+        self.path = os.path.join("/tmp", f"drs_clocks_{os.getpid()}.csv")
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def synthetic_model_and_inputs():
+    import torch
+    import common as T
+    model, sd = T.default_init_model("superres", seed=0, bn_seed=1)
+    lr = T.np_rand(2, 3, S // MAG, S // MAG)       # Sentinel-2-shaped RGB in [0, 1)
+    return model, sd, lr
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_arm(steps, warmup, budget_s, n_images=None):
+    """Times `steps` reverse steps of the oracle port on n_images of the 16-image batch (bounded sample)."""
+    import torch
+    import common as T
+    from oracle import restatement as R
+    torch.set_grad_enabled(False)
+    cores = torch.get_num_threads()
+    _, sd, lr = synthetic_model_and_inputs()
+    sched = R.noise_schedule("cosine", NOISE_STEPS)
+    cond = lr.unsqueeze(0)
+    x1 = T.np_randn(3, 1, 3, S, S)
+    t0 = time.perf_counter()
+    R.unet_forward(sd, "superres", x1, torch.tensor([NOISE_STEPS - 1]), cond, MAG)
+    t_img = time.perf_counter() - t0          # includes first-call overhead: an upper bound
+    if n_images is None:
+        n_images = int(max(1, min(BATCH, budget_s / max(1e-3, (steps + warmup) * t_img))))
+    x = T.np_randn(3, n_images, 3, S, S)
+    alpha, alpha_hat, beta = sched
+
+    def one_step(x, i):
+        t = (torch.ones(n_images) * i).long()
+        eps = R.unet_forward(sd, "superres", x, t, cond, MAG)
+        z = torch.randn_like(x)
+        return R.posterior_update(x, eps, z, alpha[t][:, None, None, None], alpha_hat[t][:, None, None, None],
+                                  beta[t][:, None, None, None])
+
+    i = NOISE_STEPS - 1
+    for _ in range(warmup):
+        x = one_step(x, i)
+        i -= 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        x = one_step(x, i)
+        i -= 1
+    dt = time.perf_counter() - t0
+    value = n_images * steps / dt
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} reverse steps (after {warmup} warm-up) of {n_images} of the {BATCH} images of {WORKLOAD}, "
+                      f"oracle/restatement.py (the torch CPU ops the reference modules call), fp32, {cores} threads",
+            "ms_per_step": 1e3 * dt / steps, "n_images": n_images}
+
+
+def run_reference(args):
+    rank, world, _ = rank_world()
+    if rank != 0:
+        return
+    cb = cpu_reference_arm(args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_step_sample": cb["n_images"], "noise_steps": NOISE_STEPS},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import common as T
+    import diffusionremotesensing_b200 as D
+    from diffusionremotesensing_b200 import _native as N
+    import ctypes as C
+
+    rank, world, local = rank_world()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = N.lib()
+
+    model, sd, lr = synthetic_model_and_inputs()
+    model.to(dev).eval()
+    K, W = args.steps, args.warmup
+    diffusion = D.Diffusion("cosine", model, "/nonexistent", noise_steps=NOISE_STEPS, device=str(dev),
+                            magnification_factor=MAG, image_size=S, Degradation_type="DownBlur")
+
+    # ---- device-resident leg: K graph-replayed steps -------------------------------------------------------
+    st = N.stream_ptr(dev)
+    plan = model.native_plan(BATCH, BATCH, 1, S, MAG)
+    lr_dev = lr.unsqueeze(0).to(dev).contiguous()
+    c1, c2, c3 = diffusion._coefficients()
+    x = T.np_randn(3 + rank, BATCH, 3, S, S).to(dev).contiguous()
+    z = torch.empty_like(x)
+    eps = torch.empty_like(x)
+    N.check(lib.drs_cond_encode(plan, N.ptr(lr_dev), st))
+    N.check(lib.drs_sampler_prepare(plan, NOISE_STEPS, N.ptr(c1), N.ptr(c2), N.ptr(c3), None, 0.0, st))
+    N.check(lib.drs_sampler_begin(plan, N.ptr(x), N.ptr(z), N.ptr(eps), NOISE_STEPS - 1, st))
+    if K + W > NOISE_STEPS - 2:
+        raise SystemExit("steps + warmup must stay below the 1499 UNet evaluations of the schedule")
+
+    def step():
+        z.normal_()
+        N.check(lib.drs_sampler_step(plan, 1, st))
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    N.check(lib.drs_plan_check(plan, st))
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    clock_info = clocks.stop() if clocks else None
+    launches_per_step = lib.drs_sampler_launches_per_step(plan)
+    value = world * BATCH * K / (ms * 1e-3)
+
+    # ---- roofline of the tensor-core launches (rank 0, live CUDA events inside the library) ----------------
+    roofline, layer_rows = None, []
+    if rank == 0:
+        n_l = lib.drs_plan_launch_count(plan)
+        ms_out = torch.zeros(n_l, dtype=torch.float32)
+        N.check(lib.drs_plan_profile(plan, N.ptr(x), N.ptr(eps), max(3, min(K, 10)), N.ptr(ms_out), st))
+        tot_f = tot_ms = 0.0
+        for i in range(n_l):
+            name = C.create_string_buffer(64)
+            fl, by, ctas, smem = C.c_double(), C.c_double(), C.c_int(), C.c_int()
+            N.check(lib.drs_plan_launch_info(plan, i, name, 64, C.byref(fl), C.byref(by), C.byref(ctas), C.byref(smem)))
+            row = {"launch": name.value.decode(), "ms": float(ms_out[i]), "gflop": fl.value / 1e9, "mbytes": by.value / 1e6,
+                   "ctas": ctas.value, "smem": smem.value}
+            row["tflops"] = row["gflop"] / max(row["ms"], 1e-9)
+            row["gbs"] = row["mbytes"] / max(row["ms"], 1e-9)
+            layer_rows.append(row)
+            if i > 0:
+                tot_f += fl.value
+                tot_ms += float(ms_out[i])
+        peaks = measured_peaks()
+        achieved = tot_f / (tot_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
+                    "kernel": "conv_gemm_kernel (all tcgen05 implicit-GEMM launches of one UNet evaluation)",
+                    "algorithmic_gflop_per_eval": tot_f / 1e9, "kernel_ms_per_eval": tot_ms,
+                    "kernel_share_of_step": tot_ms / (ms / K)}
+        if args.layers:
+            with open(args.layers, "w") as f:
+                json.dump(layer_rows, f, indent=1)
+
+    # ---- end-to-end leg through the public API with host buffers ---------------------------------------------
+    e2e = None
+    d_e2e = D.Diffusion("cosine", model, "/nonexistent", noise_steps=K + 1, device=str(dev), magnification_factor=MAG,
+                        image_size=S, Degradation_type="DownBlur")
+    lr_host = lr.clone().pin_memory()
+    xT_host = T.np_randn(5 + rank, BATCH, 3, S, S).pin_memory()
+    out_host = torch.empty((BATCH, 3, S, S), dtype=torch.float32).pin_memory()
+    d_e2e.sample(BATCH, model, lr_host, input_channels=3, x_T=xT_host)          # warm-up (plans, graphs, tables)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = d_e2e.sample(BATCH, model, lr_host, input_channels=3, x_T=xT_host)
+    out_host.copy_(res, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = t.item()
+    e2e = {"value": world * BATCH * K / dt, "unit": UNIT,
+           "h2d_bytes_per_step": (lr_host.numel() + xT_host.numel()) * 4 / K,
+           "d2h_bytes_per_step": out_host.numel() * 4 / K,
+           "call": f"Diffusion.sample(n={BATCH}, model, lr_img) with noise_steps={K + 1} ({K} UNet evaluations), pinned host in/out",
+           "seconds": dt}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cb = cpu_reference_arm(steps=3, warmup=1, budget_s=25.0)
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "image_size": S, "noise_steps": NOISE_STEPS,
+                           "l2": "activations of one step (560 MB bf16) exceed the 126 MB L2; no explicit flush",
+                           "parallelism": f"batch-sharded x{world}, no per-step collective"},
+                "steps_per_sec": world * K / (ms * 1e-3) / world, "sr_images_per_sec": value / (NOISE_STEPS - 1),
+                "clocks": clock_info, "e2e": e2e, "gpu_launches": K * launches_per_step,
+                "launches_per_step": launches_per_step, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", default=None, help="write the per-launch table (JSON) to this path")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

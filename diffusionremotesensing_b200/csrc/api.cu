@@ -22,6 +22,9 @@ int sampler_prepare(DrsPlan*, int, const float*, const float*, const float*, con
 int sampler_begin(DrsPlan*, float*, float*, float*, int, cudaStream_t);
 int sampler_step(DrsPlan*, int, cudaStream_t);
 int launches_per_step(const DrsPlan*);
+int launch_count(const DrsPlan*);
+int launch_info(const DrsPlan*, int, char*, int, double*, double*, int*, int*);
+int plan_profile(DrsPlan*, const float*, float*, int, float*, cudaStream_t);
 int debug_bind_and_run(DrsPlan*, const void*, int, int, int, int, void*, int, int, cudaStream_t);
 }  // namespace drs
 
@@ -99,6 +102,23 @@ int drs_sampler_step(DrsPlan* p, int use_graph, void* stream) {
   return sampler_step(p, use_graph, as_stream(stream));
 }
 int drs_sampler_launches_per_step(const DrsPlan* p) { return p ? launches_per_step(p) : 0; }
+
+int drs_plan_launch_count(const DrsPlan* p) { return p ? launch_count(p) : 0; }
+int drs_plan_launch_info(const DrsPlan* p, int index, char* name, int name_capacity, double* flops, double* bytes,
+                         int* ctas, int* smem_bytes) {
+  if (!p) {
+    set_error("null plan");
+    return DRS_E_INVALID;
+  }
+  return launch_info(p, index, name, name_capacity, flops, bytes, ctas, smem_bytes);
+}
+int drs_plan_profile(DrsPlan* p, const float* x_dev, float* eps_dev, int iters, float* ms_out, void* stream) {
+  if (!p) {
+    set_error("null plan");
+    return DRS_E_INVALID;
+  }
+  return plan_profile(p, x_dev, eps_dev, iters, ms_out, as_stream(stream));
+}
 
 int drs_ddpm_update(float* x_dev, const float* eps_dev, const float* noise_dev_or_null, float c1, float c2, float c3,
                     size_t numel, void* stream) {

@@ -635,4 +635,103 @@ int debug_bind_and_run(DrsPlan* p, const void* in, int gridW, int gridH, int src
 
 int launches_per_step(const DrsPlan* p) { return static_cast<int>(p->launches.size()) + 3; }
 
+// ------------------------------------------------------------------------------------------------
+// per-launch accounting (bench / profiles): algorithmic work and live CUDA-event timing
+// ------------------------------------------------------------------------------------------------
+int launch_count(const DrsPlan* p) { return static_cast<int>(p->launches.size()) + 1; }
+
+// launch 0 = conv0 (CUDA cores), launch i >= 1 = tensor-core launch i-1
+int launch_info(const DrsPlan* p, int i, char* name, int name_cap, double* flops, double* bytes, int* ctas,
+                int* smem_bytes) {
+  const DrsModel* m = p->m;
+  if (i < 0 || i >= launch_count(p)) {
+    set_error("launch index %d out of range", i);
+    return DRS_E_INVALID;
+  }
+  const double px = static_cast<double>(p->nb) * p->S * p->S;
+  if (i == 0) {
+    if (name) snprintf(name, name_cap, "conv0");
+    if (flops) *flops = 2.0 * px * 16 * 9 * m->desc.x_channels;
+    if (bytes) *bytes = static_cast<double>(p->nx) * m->desc.x_channels * p->S * p->S * 4 + px * 16 * 2 +
+                        (m->has_cond ? static_cast<double>(p->ncond) * p->S * p->S * 16 * 4 : 0.0);
+    if (ctas) *ctas = static_cast<int>((px + 127) / 128);
+    if (smem_bytes) *smem_bytes = 0;
+    return DRS_OK;
+  }
+  const Launch& L = p->launches[i - 1];
+  const GemmSpec& g = m->gemms[L.spec];
+  const double grid_px = static_cast<double>(p->nb) * L.args.H * L.args.W;
+  double macs = 0, wbytes = 0;
+  for (const KBlock& kb : g.kblocks) {
+    macs += static_cast<double>(kb.n) * kb.ck;
+    wbytes += kb.b_bytes;
+  }
+  if (name) snprintf(name, name_cap, "%s", g.name.c_str());
+  if (flops) {
+    *flops = 2.0 * grid_px * macs;
+    if (g.epi_kind == EPI_OUT) *flops += 2.0 * grid_px * g.n_sub * g.nvec;  // fused 1x1 output conv
+    if (g.epi_kind == EPI_PSI) *flops += 2.0 * grid_px * g.n_sub;
+  }
+  if (bytes) {
+    double b = wbytes;
+    for (int s = 0; s < g.n_src; ++s) {
+      const ActTensor& t = p->acts.at(g.src_name[s]);
+      b += static_cast<double>(p->nb) * t.H * t.W * t.C * 2;
+    }
+    if (g.flags & F_ROWSCALE) b += grid_px;  // psi map, fp32 at quarter resolution
+    if (g.epi_kind == EPI_OUT)
+      b += grid_px * g.nvec * 4;
+    else if (g.epi_kind == EPI_PSI)
+      b += grid_px * 4;
+    else
+      b += grid_px * g.oscale * g.oscale * g.OC * 2;
+    *bytes = b;
+  }
+  if (ctas) *ctas = L.n_tiles * g.nsplit;
+  if (smem_bytes) *smem_bytes = static_cast<int>(L.smem);
+  return DRS_OK;
+}
+
+// Runs `iters` forwards with a CUDA event between consecutive launches (on `st`, the stream the kernels are
+// launched on) and returns the mean duration of every launch in milliseconds. Synchronises the stream.
+int plan_profile(DrsPlan* p, const float* x, float* eps, int iters, float* ms_out, cudaStream_t st) {
+  if (!x || !eps || !ms_out || iters < 1) {
+    set_error("drs_plan_profile: bad arguments");
+    return DRS_E_INVALID;
+  }
+  const DrsModel* m = p->m;
+  const int n = launch_count(p);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) DRS_CUDA(cudaEventCreate(&e));
+  std::vector<double> acc(n, 0.0);
+  int rc = DRS_OK;
+  for (int it = 0; it < iters && rc == DRS_OK; ++it) {
+    const ActTensor& h0 = p->acts.at("h0");
+    cudaEventRecord(ev[0], st);
+    launch_conv0(x, m->f(m->conv0.w), m->f(m->conv0.b), m->has_cond ? p->cond_feat.as<float>() : nullptr,
+                 p->workspace.as<uint8_t>() + h0.offset, p->nb, p->nx, m->has_cond ? p->ncond : 1,
+                 m->desc.x_channels, p->S, st);
+    cudaEventRecord(ev[1], st);
+    for (size_t i = 0; i < p->launches.size(); ++i) {
+      Launch& L = p->launches[i];
+      const GemmSpec& g = m->gemms[L.spec];
+      ConvArgs a = L.args;
+      if (g.epi_kind == EPI_OUT) a.epi.out = eps;
+      const int r = launch_conv_gemm(g.epi_kind, L.map0, L.map1, a, L.n_tiles, g.nsplit, L.smem, st);
+      if (r != 0) rc = cuda_fail(static_cast<cudaError_t>(r), g.name.c_str());
+      cudaEventRecord(ev[i + 2], st);
+    }
+    const cudaError_t se = cudaStreamSynchronize(st);
+    if (se != cudaSuccess) rc = cuda_fail(se, "cudaStreamSynchronize(profile)");
+    for (int i = 0; i < n && rc == DRS_OK; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      acc[i] += ms;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  for (int i = 0; i < n; ++i) ms_out[i] = static_cast<float>(acc[i] / iters);
+  return rc;
+}
+
 }  // namespace drs

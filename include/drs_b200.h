@@ -106,6 +106,16 @@ int drs_sampler_step(DrsPlan* p, int use_graph, void* stream);
 /* Number of kernel launches one sampler step issues (bench bookkeeping). */
 int drs_sampler_launches_per_step(const DrsPlan* p);
 
+/* Per-launch accounting of one UNet evaluation (bench.py / profiles). Launch 0 is the CUDA-core conv0 kernel, the
+ * others are tensor-core launches in execution order. flops / bytes are ALGORITHMIC: 2 * MACs of the convolutions the
+ * launch computes, and one read of every input + one write of the output + the weights.
+ * drs_plan_profile runs `iters` evaluations with a CUDA event between consecutive launches on `stream` and writes
+ * the mean duration (ms) of every launch to ms_out[drs_plan_launch_count()]; it synchronises the stream. */
+int drs_plan_launch_count(const DrsPlan* p);
+int drs_plan_launch_info(const DrsPlan* p, int index, char* name, int name_capacity, double* flops, double* bytes,
+                         int* ctas, int* smem_bytes);
+int drs_plan_profile(DrsPlan* p, const float* x_dev, float* eps_dev, int iters, float* ms_out, void* stream);
+
 /* Stand-alone posterior update (train_diffusion_superres.py:240-249), scalars given directly. */
 int drs_ddpm_update(float* x_dev, const float* eps_dev, const float* noise_dev_or_null, float c1, float c2, float c3,
                     size_t numel, void* stream);
