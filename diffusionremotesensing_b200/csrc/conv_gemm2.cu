@@ -1,0 +1,243 @@
+// Persistent halo-tile tcgen05 convolution kernel (see conv_gemm2.cuh for the model).
+//
+// CTA = 192 threads, one CTA (or two, when shared memory and TMEM allow) per SM, looping over pixel tiles:
+//   warp 0 (one lane)  producer: resident weights once; per tile one 5-D TMA box per A sub-tile (halo tile of one
+//                      channel block) and, when the weights are streamed, one bulk copy per K-block
+//   warp 1 (one lane)  tcgen05.mma issuer; owns the TMEM allocation (1 or 2 accumulator buffers)
+//   warps 2..5         epilogue of the previous tile (tcgen05.ld, fused affine / ReLU / adds, global stores)
+// Rings: A slots (full/empty), B stages (full/empty, streamed mode), TMEM buffers (full/empty).
+#include "conv_epilogue.cuh"
+#include "conv_gemm2.cuh"
+#include "ptx.cuh"
+
+namespace drs {
+
+struct RingPos {
+  int idx;
+  uint32_t phase;
+  __device__ __forceinline__ void advance(int n) {
+    if (++idx == n) {
+      idx = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
+// K-major swizzled operand whose 8-row groups are `sbo16 * 16` bytes apart (rows inside a group: row_bytes apart).
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sbo(uint32_t smem_addr, uint32_t row_bytes, uint32_t sbo16) {
+  const uint64_t layout = (row_bytes == 128) ? 2ull : (row_bytes == 64) ? 4ull : 6ull;
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= 1ull << 16;
+  d |= static_cast<uint64_t>(sbo16 & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= layout << 61;
+  return d;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemm2Threads)
+conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                  const Conv2Args a) {
+  extern __shared__ uint8_t dyn_smem[];
+  __shared__ __align__(16) KBlock2 s_kb[kMaxKBlocks];
+  __shared__ __align__(16) SubTile s_st[kMaxSubTiles];
+  __shared__ __align__(8) uint64_t s_afull[kMaxASlots], s_aempty[kMaxASlots];
+  __shared__ __align__(8) uint64_t s_bfull[kMaxBStages], s_bempty[kMaxBStages];
+  __shared__ __align__(8) uint64_t s_tfull[2], s_tempty[2];
+  __shared__ __align__(8) uint64_t s_wready;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_par[4][kMaxN];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const EpiArgs& e = a.epi;
+
+  const uint32_t dyn_u32 = smem_u32(dyn_smem);
+  uint8_t* const a_base = dyn_smem + ((1024u - (dyn_u32 & 1023u)) & 1023u);
+  uint8_t* const b_base = a_base + static_cast<size_t>(a.a_slots) * a.a_slot_bytes;
+
+  const int split = blockIdx.x % a.nsplit;
+  const int first_tile = blockIdx.x / a.nsplit;
+  const int tile_step = gridDim.x / a.nsplit;
+  const int oc_off = split * a.n_sub;
+  const int nkb = a.nkb;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+
+  // ---- one-time setup --------------------------------------------------------------------------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.kblocks + static_cast<size_t>(split) * nkb);
+    uint4* dst = reinterpret_cast<uint4*>(s_kb);
+    for (int i = threadIdx.x; i < nkb * 2; i += kGemm2Threads) dst[i] = __ldg(src + i);
+    const uint4* ssrc = reinterpret_cast<const uint4*>(a.subtiles);
+    uint4* sdst = reinterpret_cast<uint4*>(s_st);
+    for (int i = threadIdx.x; i < a.n_sub_tiles; i += kGemm2Threads) sdst[i] = __ldg(ssrc + i);
+    load_epilogue_params<EPI>(e, a.n_sub, oc_off, s_par, threadIdx.x, kGemm2Threads);
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map0);
+    tma_prefetch_desc(&map1);
+    for (int s = 0; s < a.a_slots; ++s) {
+      mbar_init(&s_afull[s], 1);
+      mbar_init(&s_aempty[s], 1);
+    }
+    for (int s = 0; s < a.b_stages; ++s) {
+      mbar_init(&s_bfull[s], 1);
+      mbar_init(&s_bempty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_tfull[s], 1);
+      mbar_init(&s_tempty[s], 128);
+    }
+    mbar_init(&s_wready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&s_tmem_base, static_cast<uint32_t>(a.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem_base;
+
+  if (warp == 0) {
+    // ---- producer ------------------------------------------------------------------------------
+    if (lane == 0) {
+      if (a.resident) {
+        mbar_expect_tx(&s_wready, a.w_split_bytes);
+        const uint8_t* src = a.wpack + a.w_split_off + static_cast<size_t>(split) * a.w_split_bytes;
+        for (uint32_t off = 0; off < a.w_split_bytes; off += 16384u) {
+          const uint32_t n = min(16384u, a.w_split_bytes - off);
+          bulk_load(b_base + off, src + off, n, &s_wready);
+        }
+      }
+      RingPos ar{0, 0}, br{0, 0};
+      for (int tile = first_tile; tile < a.n_tiles; tile += tile_step) {
+        const int b = tile / tiles_per_img;
+        const int t2 = tile - b * tiles_per_img;
+        const int y0 = (t2 / a.tiles_x) * kTile2H;
+        const int x0 = (t2 % a.tiles_x) * kTile2W;
+        int st = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const KBlock2 K = s_kb[kb];
+          if (K.flags & KB2_FIRST) {
+            const SubTile T = s_st[st++];
+            mbar_wait(&s_aempty[ar.idx], ar.phase ^ 1u, a.err, 1);
+            mbar_expect_tx(&s_afull[ar.idx], T.bytes);
+            tma_load_5d(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes, T.src ? &map1 : &map0, &s_afull[ar.idx],
+                        T.c, x0 + T.dx0, 0, y0 + T.dy0, b);
+            ar.advance(a.a_slots);
+          }
+          if (!a.resident) {
+            mbar_wait(&s_bempty[br.idx], br.phase ^ 1u, a.err, 1);
+            mbar_expect_tx(&s_bfull[br.idx], K.b_bytes);
+            bulk_load(b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes, a.wpack + K.b_off, K.b_bytes,
+                      &s_bfull[br.idx]);
+            br.advance(a.b_stages);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----------------------------------------------------------------------------
+    if (lane == 0) {
+      if (a.resident) mbar_wait(&s_wready, 0, a.err, 2);
+      RingPos ar{0, 0}, br{0, 0}, tr{0, 0};
+      for (int tile = first_tile; tile < a.n_tiles; tile += tile_step) {
+        mbar_wait(&s_tempty[tr.idx], tr.phase ^ 1u, a.err, 2);
+        tc_fence_after();
+        const uint32_t acc = tmem + static_cast<uint32_t>(tr.idx * a.acc_cols);
+        uint32_t slot_addr = 0;
+        int cur_slot = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const KBlock2 K = s_kb[kb];
+          if (K.flags & KB2_FIRST) {
+            mbar_wait(&s_afull[ar.idx], ar.phase, a.err, 2);
+            cur_slot = ar.idx;
+            slot_addr = smem_u32(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes);
+            ar.advance(a.a_slots);
+          }
+          uint32_t sb;
+          if (a.resident) {
+            sb = smem_u32(b_base) + K.b_off;
+          } else {
+            mbar_wait(&s_bfull[br.idx], br.phase, a.err, 2);
+            sb = smem_u32(b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes);
+          }
+          tc_fence_after();
+          const uint32_t row_bytes = K.ck * 2u;
+          const uint64_t da = umma_desc_kmajor_sbo(slot_addr + K.a_off, row_bytes, K.sbo16);
+          const uint64_t db = umma_desc_kmajor(sb, row_bytes);
+          const uint32_t idesc = umma_idesc_bf16(kTileM, K.n);
+          const int nk = K.ck >> 4;
+          for (int k = 0; k < nk; ++k)
+            umma_bf16(acc + K.col, da + 2u * k, db + 2u * k, idesc, ((K.flags & KB2_INIT) && k == 0) ? 0u : 1u);
+          if (!a.resident) {
+            umma_commit(&s_bempty[br.idx]);
+            br.advance(a.b_stages);
+          }
+          if (K.flags & KB2_LAST) umma_commit(&s_aempty[cur_slot]);
+        }
+        umma_commit(&s_tfull[tr.idx]);
+        tr.advance(a.acc_bufs);
+      }
+    }
+  } else {
+    // ---- epilogue ------------------------------------------------------------------------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int lx = row & (kTile2W - 1);
+    const int ly = row >> 3;
+    RingPos tr{0, 0};
+    for (int tile = first_tile; tile < a.n_tiles; tile += tile_step) {
+      const int b = tile / tiles_per_img;
+      const int t2 = tile - b * tiles_per_img;
+      const int y = (t2 / a.tiles_x) * kTile2H + ly;
+      const int x = (t2 % a.tiles_x) * kTile2W + lx;
+      const bool valid = (x < a.W) && (y < a.H);
+      mbar_wait(&s_tfull[tr.idx], tr.phase, a.err, 3);
+      tc_fence_after();
+      const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(tr.idx * a.acc_cols);
+      conv_epilogue<EPI>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par);
+      tc_fence_before();
+      mbar_arrive(&s_tempty[tr.idx]);
+      tr.advance(a.acc_bufs);
+    }
+  }
+
+  // ---- teardown ----------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, static_cast<uint32_t>(a.tmem_cols));
+  }
+}
+
+static constexpr int kMaxDynSmem2 = 220 * 1024;
+
+int conv_gemm2_set_smem_limits() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(conv_gemm2_kernel<EPI_STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem2);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(conv_gemm2_kernel<EPI_PSI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem2);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(conv_gemm2_kernel<EPI_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem2);
+  return static_cast<int>(e);
+}
+
+int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& map1, const Conv2Args& args, int grid,
+                      size_t smem_bytes, cudaStream_t stream) {
+  dim3 g(static_cast<unsigned>(grid), 1, 1);
+  dim3 block(kGemm2Threads, 1, 1);
+  switch (epi_kind) {
+    case EPI_STD: conv_gemm2_kernel<EPI_STD><<<g, block, smem_bytes, stream>>>(map0, map1, args); break;
+    case EPI_PSI: conv_gemm2_kernel<EPI_PSI><<<g, block, smem_bytes, stream>>>(map0, map1, args); break;
+    case EPI_OUT: conv_gemm2_kernel<EPI_OUT><<<g, block, smem_bytes, stream>>>(map0, map1, args); break;
+    default: return static_cast<int>(cudaErrorInvalidValue);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace drs

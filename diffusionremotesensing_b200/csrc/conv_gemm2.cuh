@@ -1,0 +1,80 @@
+// Persistent halo-tile implicit-GEMM convolution (second-generation kernel), shared host/device declarations.
+//
+// conv_gemm.cu re-reads the 128-pixel activation tile from L2 once per filter tap, which makes the full-resolution
+// layers L2->SM bandwidth bound. Here a CTA loads, per 64/32/16-channel block, ONE halo tile
+// ((8 + halo) x (16 + halo) pixels, pixel-major, hardware swizzled) and every filter tap is an MMA whose A
+// descriptor starts at a different pixel of that tile:
+//     row m = 8 g + r of the MMA  <->  pixel (x0 + r, y0 + g);  address = start + g * SBO + r * pixel_bytes
+// with SBO = halo_width * pixel_bytes, so a tap shift (dx, dy) is just start += (dy * halo_width + dx) * pixel_bytes.
+// CTAs are persistent (static round-robin over pixel tiles), keep the layer's weights resident in shared memory when
+// they fit (else stream them through a ring per tile) and double-buffer the TMEM accumulator so the epilogue of tile
+// i overlaps the MMAs of tile i + 1.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "conv_gemm.cuh"
+
+namespace drs {
+
+constexpr int kTile2W = 8;    // pixels per accumulator row group (fixed by the UMMA 8-row core-matrix group)
+constexpr int kTile2H = 16;   // row groups per M = 128 tile
+constexpr int kGemm2Threads = 192;
+constexpr int kMaxSubTiles = 16;
+constexpr int kMaxASlots = 8;
+constexpr int kMaxBStages = 8;
+
+struct __align__(16) KBlock2 {
+  uint32_t a_off;     // byte offset of the tap's first pixel inside its A sub-tile
+  uint32_t b_off;     // streamed: byte offset in the global weight blob; resident: byte offset in the smem image
+  uint32_t b_bytes;   // n * ck * 2
+  uint16_t n;         // MMA N
+  uint16_t col;       // accumulator column offset inside one TMEM buffer
+  uint16_t sbo16;     // A descriptor stride between 8-row groups, in 16-byte units
+  uint8_t ck;         // channels of this K-block: 16 / 32 / 64
+  uint8_t flags;      // KB2_*
+  uint32_t pad[3];
+};
+static_assert(sizeof(KBlock2) == 32, "KBlock2 must be 32 bytes");
+
+enum : uint8_t {
+  KB2_INIT = 1,   // first K-block writing these accumulator columns: overwrite
+  KB2_FIRST = 2,  // first K-block of an A sub-tile: acquire the next A slot
+  KB2_LAST = 4,   // last K-block of an A sub-tile: release the slot
+};
+
+struct __align__(16) SubTile {
+  int32_t c;        // coordinate 0 of the TMA box (channel block, plus px * C for stride-2 views)
+  int16_t dx0, dy0; // halo origin relative to the tile origin (coordinates 1 and 3)
+  uint32_t bytes;   // box bytes = ck * 2 * halo_w * npy * halo_h
+  uint8_t src;      // tensor map 0 / 1
+  uint8_t pad[3];
+};
+static_assert(sizeof(SubTile) == 16, "SubTile must be 16 bytes");
+
+struct Conv2Args {
+  const KBlock2* kblocks;   // [nsplit][nkb]
+  const SubTile* subtiles;  // [n_sub_tiles] (same for every split)
+  const uint8_t* wpack;     // weight blob (v2 packing)
+  uint32_t w_split_off;     // resident: byte offset of split 0's image inside wpack
+  uint32_t w_split_bytes;   // resident: bytes of one split's image (multiple of 1024)
+  int nkb, n_sub_tiles;
+  int resident;             // 1: weights loaded once per CTA
+  int W, H, B;              // output pixel grid
+  int tiles_x, tiles_y, n_tiles;
+  int a_slots, a_slot_bytes;
+  int b_stages, b_stage_bytes;
+  int tmem_cols;            // allocation (power of two)
+  int acc_cols;             // columns one tile's accumulators use
+  int acc_bufs;             // 1 or 2
+  int n_sub, nsplit;
+  int* err;
+  EpiArgs epi;
+};
+
+int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& map1, const Conv2Args& args, int grid,
+                      size_t smem_bytes, cudaStream_t stream);
+int conv_gemm2_set_smem_limits();
+
+}  // namespace drs

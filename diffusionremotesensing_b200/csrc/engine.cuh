@@ -14,6 +14,7 @@
 
 #include "../../include/drs_b200.h"
 #include "conv_gemm.cuh"
+#include "conv_gemm2.cuh"
 
 namespace drs {
 
@@ -89,6 +90,20 @@ struct GemmSpec {
   int nvec = 0;
   int te_off = 0, pre_off = 0;
   size_t kb_dev_off = 0;  // offset (in KBlocks) into the model's device K-block array
+
+  // second-generation (persistent halo-tile) program of the same launch, see conv_gemm2.cuh
+  struct V2 {
+    bool usable = false;
+    bool resident = false;            // weights of one split fit in shared memory
+    int nkb = 0;
+    std::vector<KBlock2> kblocks;     // [nsplit][nkb]
+    std::vector<SubTile> subtiles;
+    int halo_w[2] = {0, 0}, halo_h[2] = {0, 0}, npy[2] = {1, 1};   // TMA box geometry per source
+    int a_slot_bytes = 0, b_stage_bytes = 0;
+    int acc_cols = 0;
+    uint32_t w_split_off = 0, w_split_bytes = 0;
+    size_t kb_dev_off = 0, st_dev_off = 0;
+  } v2;
 };
 
 struct TimeMlp {
@@ -113,7 +128,9 @@ struct DrsModel {
   std::vector<float> fblob;                      // fp32 parameters (host staging)
   std::vector<uint8_t> wblob;                    // bf16 swizzled weight tiles (host staging)
   std::vector<drs::KBlock> kb_all;
-  drs::DevMem d_fblob, d_wblob, d_kblocks;
+  std::vector<drs::KBlock2> kb2_all;
+  std::vector<drs::SubTile> st_all;
+  drs::DevMem d_fblob, d_wblob, d_kblocks, d_kblocks2, d_subtiles;
   std::vector<drs::GemmSpec> gemms;              // in execution order
   drs::TimeMlp mlps[7];                          // conv_blocks.0-2, bottle_neck, ups.0-2
   int te_stride = 0;
@@ -140,6 +157,9 @@ struct Launch {
   ConvArgs args;
   int n_tiles = 0;
   size_t smem = 0;
+  bool use_v2 = false;
+  Conv2Args args2;
+  int grid2 = 0;
 };
 
 }  // namespace drs

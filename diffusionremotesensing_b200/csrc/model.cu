@@ -242,7 +242,143 @@ struct Builder {
     g.tmem_cols = pow2_at_least(max_col, 32);
     g.kb_dev_off = m->kb_all.size();
     m->kb_all.insert(m->kb_all.end(), g.kblocks.begin(), g.kblocks.end());
+    build_v2(g, terms);
     return true;
+  }
+
+  // Halo-tile program of the same launch (conv_gemm2.cuh). K-blocks are ordered sub-tile major: all taps that read
+  // one (source, channel block[, column parity]) halo tile are consecutive, so the tile is loaded once.
+  void build_v2(GemmSpec& g, const std::vector<ConvTerm>& terms) {
+    GemmSpec::V2& v = g.v2;
+    v.usable = false;
+    bool src_seen[2] = {false, false};
+    for (const ConvTerm& t : terms) {
+      if (src_seen[t.src]) return;  // one convolution per source tensor only
+      src_seen[t.src] = true;
+    }
+    // halo geometry per kind
+    struct Geo { int dx_min, dy_min, hw, hh, npy; };
+    auto geo_of = [](int kind) -> Geo {
+      switch (kind) {
+        case CONV_3x3: return {-1, -1, kTile2W + 2, kTile2H + 2, 1};
+        case CONV_3x3_S2: return {-1, -1, kTile2W + 1, kTile2H + 1, 2};
+        case CONV_1x1: return {0, 0, kTile2W, kTile2H, 1};
+        case CONV_2x2_S2: return {0, 0, kTile2W, kTile2H, 2};
+        default: return {0, 0, kTile2W + 1, kTile2H + 1, 1};  // CONV_T3x3_S2: taps at (0 / +1)
+      }
+    };
+    // pass 1: sizes (identical for every split)
+    size_t w_image = 0;
+    int max_col = 0, max_b = 0, max_a = 0;
+    for (const ConvTerm& t : terms) {
+      const int ck = g.src_ck[t.src];
+      const Geo G = geo_of(t.kind);
+      v.halo_w[t.src] = G.hw;
+      v.halo_h[t.src] = G.hh;
+      v.npy[t.src] = G.npy;
+      max_a = std::max(max_a, ck * 2 * G.hw * G.hh * G.npy);
+      const int n = g.n_sub * static_cast<int>(t.stack.size());
+      const size_t tile_bytes = (static_cast<size_t>(n) * ck * 2 + 1023) & ~static_cast<size_t>(1023);
+      w_image += tile_bytes * taps_of(t.kind).size() * (t.C / ck);
+      max_b = std::max(max_b, n * ck * 2);
+    }
+    v.a_slot_bytes = (max_a + 1023) & ~1023;
+    v.b_stage_bytes = (max_b + 1023) & ~1023;
+    // resident when the split's image plus two A slots leaves a CTA within ~200 KB
+    v.resident = (w_image + 2 * static_cast<size_t>(v.a_slot_bytes) <= 200 * 1024);
+    v.w_split_bytes = static_cast<uint32_t>(w_image);
+    while (m->wblob.size() % 1024) m->wblob.push_back(0);
+    v.w_split_off = static_cast<uint32_t>(m->wblob.size());
+    if (v.resident) m->wblob.resize(m->wblob.size() + w_image * g.nsplit);
+
+    v.kblocks.clear();
+    v.subtiles.clear();
+    for (int s = 0; s < g.nsplit; ++s) {
+      std::set<int> seen;
+      int count = 0;
+      size_t image_off = 0;  // offset inside this split's resident image
+      for (const ConvTerm& t : terms) {
+        const int ck = g.src_ck[t.src];
+        const int pix = ck * 2;
+        const Geo G = geo_of(t.kind);
+        const uint32_t mask = static_cast<uint32_t>(pix / 16 - 1);
+        const bool transposed = (t.kind == CONV_T3x3_S2);
+        const int kh = (t.kind == CONV_1x1) ? 1 : (t.kind == CONV_2x2_S2 ? 2 : 3);
+        const std::vector<Tap> taps = taps_of(t.kind);
+        const int n = g.n_sub * static_cast<int>(t.stack.size());
+        const int n_px = (t.kind == CONV_3x3_S2 || t.kind == CONV_2x2_S2) ? 2 : 1;
+        for (int px = 0; px < n_px; ++px) {
+          for (int c0 = 0; c0 < t.C; c0 += ck) {
+            std::vector<const Tap*> mine;
+            for (const Tap& tp : taps)
+              if (tp.px == px) mine.push_back(&tp);
+            if (mine.empty()) continue;
+            if (s == 0) {
+              SubTile st{};
+              st.c = px * t.C + c0;
+              st.dx0 = static_cast<int16_t>(G.dx_min);
+              st.dy0 = static_cast<int16_t>(G.dy_min);
+              st.bytes = static_cast<uint32_t>(pix * G.hw * G.hh * G.npy);
+              st.src = static_cast<uint8_t>(t.src);
+              v.subtiles.push_back(st);
+            }
+            for (size_t ti = 0; ti < mine.size(); ++ti) {
+              const Tap& tp = *mine[ti];
+              KBlock2 kb{};
+              kb.a_off = static_cast<uint32_t>(((tp.dx - G.dx_min) + G.hw * (tp.py + G.npy * (tp.dy - G.dy_min))) * pix);
+              kb.n = static_cast<uint16_t>(n);
+              const int col = (t.col_slot + tp.group) * g.n_sub;
+              kb.col = static_cast<uint16_t>(col);
+              kb.sbo16 = static_cast<uint16_t>(G.hw * G.npy * pix / 16);
+              kb.ck = static_cast<uint8_t>(ck);
+              kb.flags = 0;
+              if (seen.insert(col).second) kb.flags |= KB2_INIT;
+              if (ti == 0) kb.flags |= KB2_FIRST;
+              if (ti + 1 == mine.size()) kb.flags |= KB2_LAST;
+              max_col = std::max(max_col, col + n);
+              kb.b_bytes = static_cast<uint32_t>(n * pix);
+              uint8_t* tile;
+              if (v.resident) {
+                kb.b_off = static_cast<uint32_t>(image_off);
+                tile = m->wblob.data() + v.w_split_off + static_cast<size_t>(s) * w_image + image_off;
+                image_off += (static_cast<size_t>(kb.b_bytes) + 1023) & ~static_cast<size_t>(1023);
+              } else {
+                while (m->wblob.size() % 128) m->wblob.push_back(0);
+                kb.b_off = static_cast<uint32_t>(m->wblob.size());
+                m->wblob.resize(m->wblob.size() + kb.b_bytes);
+                tile = m->wblob.data() + kb.b_off;
+              }
+              for (int r = 0; r < n; ++r) {
+                const WeightRef& wr = t.stack[r / g.n_sub];
+                const int oc = s * g.n_sub + (r % g.n_sub);
+                for (int k = 0; k < ck; ++k) {
+                  const int ci = wr.ci_off + c0 + k;
+                  float val;
+                  if (transposed)
+                    val = wr.w[((static_cast<size_t>(ci) * wr.oc + oc) * 3 + tp.ky) * 3 + tp.kx];
+                  else
+                    val = wr.w[((static_cast<size_t>(oc) * wr.cin_total + ci) * kh + tp.ky) * kh + tp.kx];
+                  uint32_t o = static_cast<uint32_t>(r * pix + k * 2);
+                  o ^= ((o >> 7) & mask) << 4;
+                  const uint16_t h = f32_to_bf16(val);
+                  memcpy(tile + o, &h, 2);
+                }
+              }
+              v.kblocks.push_back(kb);
+              ++count;
+            }
+          }
+        }
+      }
+      if (s == 0) v.nkb = count;
+    }
+    if (v.nkb > kMaxKBlocks || static_cast<int>(v.subtiles.size()) > kMaxSubTiles || max_col > 512) return;
+    v.acc_cols = max_col;
+    v.kb_dev_off = m->kb2_all.size();
+    m->kb2_all.insert(m->kb2_all.end(), v.kblocks.begin(), v.kblocks.end());
+    v.st_dev_off = m->st_all.size();
+    m->st_all.insert(m->st_all.end(), v.subtiles.begin(), v.subtiles.end());
+    v.usable = true;
   }
 };
 
@@ -640,7 +776,10 @@ int model_create(const DrsModelDesc* desc, const DrsTensor* tensors, int n_tenso
   DRS_TRY(m->d_fblob.upload(m->fblob.data(), m->fblob.size() * sizeof(float)));
   DRS_TRY(m->d_wblob.upload(m->wblob.data(), m->wblob.size()));
   DRS_TRY(m->d_kblocks.upload(m->kb_all.data(), m->kb_all.size() * sizeof(KBlock)));
-  const int r = conv_gemm_set_smem_limits();
+  DRS_TRY(m->d_kblocks2.upload(m->kb2_all.data(), m->kb2_all.size() * sizeof(KBlock2)));
+  DRS_TRY(m->d_subtiles.upload(m->st_all.data(), m->st_all.size() * sizeof(SubTile)));
+  int r = conv_gemm_set_smem_limits();
+  if (r == 0) r = conv_gemm2_set_smem_limits();
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "cudaFuncSetAttribute(conv_gemm_kernel)");
   // the host copy of the state_dict is no longer needed
   m->sd.clear();
@@ -683,7 +822,10 @@ int build_debug_conv(DrsModel* m, const float* w, const float* bias, const float
   DRS_TRY(m->d_fblob.upload(m->fblob.data(), m->fblob.size() * sizeof(float)));
   DRS_TRY(m->d_wblob.upload(m->wblob.data(), m->wblob.size()));
   DRS_TRY(m->d_kblocks.upload(m->kb_all.data(), m->kb_all.size() * sizeof(KBlock)));
-  const int r = conv_gemm_set_smem_limits();
+  DRS_TRY(m->d_kblocks2.upload(m->kb2_all.data(), m->kb2_all.size() * sizeof(KBlock2)));
+  DRS_TRY(m->d_subtiles.upload(m->st_all.data(), m->st_all.size() * sizeof(SubTile)));
+  int r = conv_gemm_set_smem_limits();
+  if (r == 0) r = conv_gemm2_set_smem_limits();
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "cudaFuncSetAttribute(conv_gemm_kernel)");
   return DRS_OK;
 }
