@@ -25,6 +25,7 @@ int launches_per_step(const DrsPlan*);
 int launch_count(const DrsPlan*);
 int launch_info(const DrsPlan*, int, char*, int, double*, double*, int*, int*);
 int plan_profile(DrsPlan*, const float*, float*, int, float*, cudaStream_t);
+int mma_rate(int, int, int, int, long long*);
 int debug_bind_and_run(DrsPlan*, const void*, int, int, int, int, void*, int, int, cudaStream_t);
 }  // namespace drs
 
@@ -251,6 +252,18 @@ int drs_debug_conv2d(const float* x_dev, const float* w_host, const float* bias_
   DRS_TRY(debug_bind_and_run(p.get(), in_bf.p, gw, gh, H, W, out_bf.p, OH, OW, st));
   DRS_CUDA(static_cast<cudaError_t>(launch_nhwc_bf16_to_nchw(out_bf.p, y_dev, B, Cout, OH, OW, st)));
   DRS_TRY(check_pipeline_error(p.get(), st));
+  return DRS_OK;
+}
+
+int drs_debug_mma_rate(int n, int iters, int unroll4, int ctas_per_sm, long long* out_host) {
+  const int r = mma_rate(n, iters, unroll4, ctas_per_sm, out_host);
+  if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "mma_rate_kernel");
+  return DRS_OK;
+}
+
+int drs_debug_timeline(long long* out_host, int n) {
+  const int r = conv_gemm2_read_timeline(out_host, n);
+  if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "cudaMemcpyFromSymbol(g_timeline)");
   return DRS_OK;
 }
 

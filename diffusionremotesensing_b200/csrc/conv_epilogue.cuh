@@ -13,6 +13,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ void ld16_shared(const float* src, float* dst) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = s4[q];
+    dst[4 * q + 0] = t.x;
+    dst[4 * q + 1] = t.y;
+    dst[4 * q + 2] = t.z;
+    dst[4 * q + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void ld16_global(const float* src, float* dst) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = __ldg(s4 + q);
+    dst[4 * q + 0] = t.x;
+    dst[4 * q + 1] = t.y;
+    dst[4 * q + 2] = t.z;
+    dst[4 * q + 3] = t.w;
+  }
+}
+
 // taddr: TMEM address of this thread's lane quadrant at column 0 of the tile's accumulator.
 // (x, y, b): output-grid pixel of this thread; valid: inside the grid; W, H: grid size; N: channels of this
 // grid.y slice; oc_off: first output channel of the slice; s_par: [4][kMaxN] = scale, bias, scale2 | wvec, bias2.
@@ -41,24 +64,45 @@ __device__ __forceinline__ void conv_epilogue(const EpiArgs& e, uint32_t taddr, 
                             ((static_cast<size_t>(b) * e.OH + oy) * e.OW + ox) * e.OC + oc_off;
       const uint32_t colbase = static_cast<uint32_t>(g * N);
       for (int c0 = 0; c0 < N; c0 += 16) {
-        float v[16], w[16];
+        float v[16], w[16], p[16];
         tmem_ld16(taddr + colbase + c0, v);
         if (flags & (F_DUAL_PRE | F_DUAL_POST)) tmem_ld16(taddr + e.col2 + c0, w);
+        // per-channel vectors as 128-bit loads, issued before the TMEM wait so their latency overlaps
+        float sc[16], bi[16];
+        ld16_shared(&s_par[0][c0], sc);
+        ld16_shared(&s_par[1][c0], bi);
+        if (flags & F_PRE) ld16_global(te_pre + c0, p);
         tmem_ld_wait();
-        uint32_t pk[8];
+        if (flags & F_ROWSCALE) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = c0 + i;
-          float t = v[i];
-          if (flags & F_ROWSCALE) t *= rs;
-          if (flags & F_PRE) t += valid ? __ldg(te_pre + c) : 0.0f;
-          t = fmaf(t, s_par[0][c], s_par[1][c]);
-          if (flags & F_DUAL_PRE) t = fmaf(w[i], s_par[2][c], t);
-          if (flags & F_RELU) t = fmaxf(t, 0.0f);
-          if (flags & F_DUAL_POST) t += w[i] + s_par[3][c];
-          if (flags & F_TE) t += valid ? __ldg(te_post + c) : 0.0f;
-          v[i] = t;
+          for (int i = 0; i < 16; ++i) v[i] *= rs;
         }
+        if (flags & F_PRE) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += p[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], sc[i], bi[i]);
+        if (flags & F_DUAL_PRE) {
+          ld16_shared(&s_par[2][c0], sc);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaf(w[i], sc[i], v[i]);
+        }
+        if (flags & F_RELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        if (flags & F_DUAL_POST) {
+          ld16_shared(&s_par[3][c0], bi);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += w[i] + bi[i];
+        }
+        if (flags & F_TE) {
+          ld16_global(te_post + c0, p);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += p[i];
+        }
+        uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
         if (valid) {

@@ -25,7 +25,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
   __shared__ __align__(8) uint64_t s_empty[kMaxStages];
   __shared__ __align__(8) uint64_t s_tmem_full;
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_par[4][kMaxN];  // scale, bias, scale2 (or wvec), bias2
+  __shared__ __align__(16) float s_par[4][kMaxN];  // scale, bias, scale2 (or wvec), bias2
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

@@ -12,6 +12,15 @@
 
 namespace drs {
 
+// Debug timeline (DRS_V2_TIMELINE=1): CTA 0 records SM-clock stamps of its first tiles, 8 slots per tile:
+// 0 producer tile start, 1 producer last issue, 2 MMA after tmem-empty wait, 3 MMA after first A-full wait,
+// 4 MMA after last issue, 5 epilogue after tmem-full wait, 6 epilogue done.
+__device__ long long g_timeline[64 * 8];
+#define TL(tile_no, slot)                                                                       \
+  do {                                                                                          \
+    if (a.timeline && blockIdx.x == 0 && (tile_no) < 64) g_timeline[(tile_no) * 8 + (slot)] = clock64(); \
+  } while (0)
+
 struct RingPos {
   int idx;
   uint32_t phase;
@@ -47,9 +56,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   __shared__ __align__(8) uint64_t s_tfull[2], s_tempty[2];
   __shared__ __align__(8) uint64_t s_wready;
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_par[4][kMaxN];
+  __shared__ __align__(16) float s_par[4][kMaxN];
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
   const EpiArgs& e = a.epi;
 
@@ -102,86 +111,98 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   const uint32_t tmem = s_tmem_base;
 
   if (warp == 0) {
-    // ---- producer ------------------------------------------------------------------------------
-    if (lane == 0) {
-      if (a.resident) {
-        mbar_expect_tx(&s_wready, a.w_split_bytes);
-        const uint8_t* src = a.wpack + a.w_split_off + static_cast<size_t>(split) * a.w_split_bytes;
-        for (uint32_t off = 0; off < a.w_split_bytes; off += 16384u) {
-          const uint32_t n = min(16384u, a.w_split_bytes - off);
-          bulk_load(b_base + off, src + off, n, &s_wready);
-        }
+    // ---- producer (whole warp walks the program, one elected lane issues) -------------------------
+    if (a.resident && elect_one()) {
+      mbar_expect_tx(&s_wready, a.w_split_bytes);
+      const uint8_t* src = a.wpack + a.w_split_off + static_cast<size_t>(split) * a.w_split_bytes;
+      for (uint32_t off = 0; off < a.w_split_bytes; off += 16384u) {
+        const uint32_t n = min(16384u, a.w_split_bytes - off);
+        bulk_load(b_base + off, src + off, n, &s_wready);
       }
-      RingPos ar{0, 0}, br{0, 0};
-      for (int tile = first_tile; tile < a.n_tiles; tile += tile_step) {
-        const int b = tile / tiles_per_img;
-        const int t2 = tile - b * tiles_per_img;
-        const int y0 = (t2 / a.tiles_x) * kTile2H;
-        const int x0 = (t2 % a.tiles_x) * kTile2W;
-        int st = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-          const KBlock2 K = s_kb[kb];
-          if (K.flags & KB2_FIRST) {
-            const SubTile T = s_st[st++];
-            mbar_wait(&s_aempty[ar.idx], ar.phase ^ 1u, a.err, 1);
+    }
+    __syncwarp();
+    RingPos ar{0, 0}, br{0, 0};
+    int tno = 0;
+    for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++tno) {
+      const int b = tile / tiles_per_img;
+      const int t2 = tile - b * tiles_per_img;
+      const int y0 = (t2 / a.tiles_x) * kTile2H;
+      const int x0 = (t2 % a.tiles_x) * kTile2W;
+      int st = 0;
+      TL(tno, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const uint32_t flags = s_kb[kb].flags;
+        if (flags & KB2_FIRST) {
+          const SubTile T = s_st[st++];
+          mbar_wait(&s_aempty[ar.idx], ar.phase ^ 1u, a.err, 1);
+          if (elect_one()) {
             mbar_expect_tx(&s_afull[ar.idx], T.bytes);
             tma_load_5d(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes, T.src ? &map1 : &map0, &s_afull[ar.idx],
                         T.c, x0 + T.dx0, 0, y0 + T.dy0, b);
-            ar.advance(a.a_slots);
           }
-          if (!a.resident) {
-            mbar_wait(&s_bempty[br.idx], br.phase ^ 1u, a.err, 1);
-            mbar_expect_tx(&s_bfull[br.idx], K.b_bytes);
-            bulk_load(b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes, a.wpack + K.b_off, K.b_bytes,
-                      &s_bfull[br.idx]);
-            br.advance(a.b_stages);
+          __syncwarp();
+          ar.advance(a.a_slots);
+        }
+        if (!a.resident) {
+          const uint32_t b_off = s_kb[kb].b_off, b_bytes = s_kb[kb].b_bytes;
+          mbar_wait(&s_bempty[br.idx], br.phase ^ 1u, a.err, 1);
+          if (elect_one()) {
+            mbar_expect_tx(&s_bfull[br.idx], b_bytes);
+            bulk_load(b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes, a.wpack + b_off, b_bytes, &s_bfull[br.idx]);
           }
+          __syncwarp();
+          br.advance(a.b_stages);
         }
       }
+      TL(tno, 1);
     }
   } else if (warp == 1) {
-    // ---- MMA issuer ----------------------------------------------------------------------------
-    if (lane == 0) {
-      if (a.resident) mbar_wait(&s_wready, 0, a.err, 2);
-      RingPos ar{0, 0}, br{0, 0}, tr{0, 0};
-      for (int tile = first_tile; tile < a.n_tiles; tile += tile_step) {
-        mbar_wait(&s_tempty[tr.idx], tr.phase ^ 1u, a.err, 2);
+    // ---- MMA issuer (whole warp walks the program, one elected lane issues) -----------------------
+    if (a.resident) mbar_wait(&s_wready, 0, a.err, 2);
+    RingPos ar{0, 0}, br{0, 0}, tr{0, 0};
+    const uint32_t b_base16 = smem_u32(b_base) >> 4;
+    int tno = 0;
+    for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++tno) {
+      mbar_wait(&s_tempty[tr.idx], tr.phase ^ 1u, a.err, 2);
+      tc_fence_after();
+      TL(tno, 2);
+      const uint32_t acc = tmem + static_cast<uint32_t>(tr.idx * a.acc_cols);
+      uint32_t slot16 = 0;
+      int cur_slot = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const KBlock2 K = s_kb[kb];
+        if (K.flags & KB2_FIRST) {
+          mbar_wait(&s_afull[ar.idx], ar.phase, a.err, 2);
+          if (kb == 0) TL(tno, 3);
+          cur_slot = ar.idx;
+          slot16 = smem_u32(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes) >> 4;
+          ar.advance(a.a_slots);
+        }
+        uint32_t sb16;
+        if (a.resident) {
+          sb16 = b_base16 + (K.b_off >> 4);
+        } else {
+          mbar_wait(&s_bfull[br.idx], br.phase, a.err, 2);
+          sb16 = b_base16 + static_cast<uint32_t>((br.idx * a.b_stage_bytes) >> 4);
+        }
         tc_fence_after();
-        const uint32_t acc = tmem + static_cast<uint32_t>(tr.idx * a.acc_cols);
-        uint32_t slot_addr = 0;
-        int cur_slot = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-          const KBlock2 K = s_kb[kb];
-          if (K.flags & KB2_FIRST) {
-            mbar_wait(&s_afull[ar.idx], ar.phase, a.err, 2);
-            cur_slot = ar.idx;
-            slot_addr = smem_u32(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes);
-            ar.advance(a.a_slots);
-          }
-          uint32_t sb;
-          if (a.resident) {
-            sb = smem_u32(b_base) + K.b_off;
-          } else {
-            mbar_wait(&s_bfull[br.idx], br.phase, a.err, 2);
-            sb = smem_u32(b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes);
-          }
-          tc_fence_after();
-          const uint32_t row_bytes = K.ck * 2u;
-          const uint64_t da = umma_desc_kmajor_sbo(slot_addr + K.a_off, row_bytes, K.sbo16);
-          const uint64_t db = umma_desc_kmajor(sb, row_bytes);
-          const uint32_t idesc = umma_idesc_bf16(kTileM, K.n);
-          const int nk = K.ck >> 4;
-          for (int k = 0; k < nk; ++k)
-            umma_bf16(acc + K.col, da + 2u * k, db + 2u * k, idesc, ((K.flags & KB2_INIT) && k == 0) ? 0u : 1u);
-          if (!a.resident) {
-            umma_commit(&s_bempty[br.idx]);
-            br.advance(a.b_stages);
-          }
+        if (elect_one()) {
+          const uint32_t a_lo = ((slot16 + K.a_off16) & 0x3FFFu) | 0x10000u;
+          const uint32_t b_lo = (sb16 & 0x3FFFu) | 0x10000u;
+          const uint32_t d = acc + K.col;
+          umma_bf16_split(d, a_lo, K.desc_hi_a, b_lo, K.desc_hi_b, K.idesc, (K.flags & KB2_INIT) ? 0u : 1u);
+          for (uint32_t k = 1; k < K.nk; ++k)
+            umma_bf16_split(d, a_lo + 2u * k, K.desc_hi_a, b_lo + 2u * k, K.desc_hi_b, K.idesc, 1u);
+          if (!a.resident) umma_commit(&s_bempty[br.idx]);
           if (K.flags & KB2_LAST) umma_commit(&s_aempty[cur_slot]);
         }
-        umma_commit(&s_tfull[tr.idx]);
-        tr.advance(a.acc_bufs);
+        __syncwarp();
+        if (!a.resident) br.advance(a.b_stages);
       }
+      if (elect_one()) umma_commit(&s_tfull[tr.idx]);
+      __syncwarp();
+      TL(tno, 4);
+      tr.advance(a.acc_bufs);
     }
   } else {
     // ---- epilogue ------------------------------------------------------------------------------
@@ -190,7 +211,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     const int lx = row & (kTile2W - 1);
     const int ly = row >> 3;
     RingPos tr{0, 0};
-    for (int tile = first_tile; tile < a.n_tiles; tile += tile_step) {
+    int tno = 0;
+    for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++tno) {
       const int b = tile / tiles_per_img;
       const int t2 = tile - b * tiles_per_img;
       const int y = (t2 / a.tiles_x) * kTile2H + ly;
@@ -198,10 +220,12 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       const bool valid = (x < a.W) && (y < a.H);
       mbar_wait(&s_tfull[tr.idx], tr.phase, a.err, 3);
       tc_fence_after();
+      if (threadIdx.x == 64) TL(tno, 5);
       const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(tr.idx * a.acc_cols);
       conv_epilogue<EPI>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par);
       tc_fence_before();
       mbar_arrive(&s_tempty[tr.idx]);
+      if (threadIdx.x == 64) TL(tno, 6);
       tr.advance(a.acc_bufs);
     }
   }
@@ -227,6 +251,11 @@ int conv_gemm2_set_smem_limits() {
   return static_cast<int>(e);
 }
 
+int conv_gemm2_read_timeline(long long* host, int n) {
+  if (n > 64 * 8) n = 64 * 8;
+  return static_cast<int>(cudaMemcpyFromSymbol(host, g_timeline, n * sizeof(long long)));
+}
+
 int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& map1, const Conv2Args& args, int grid,
                       size_t smem_bytes, cudaStream_t stream) {
   dim3 g(static_cast<unsigned>(grid), 1, 1);
@@ -238,6 +267,85 @@ int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& 
     default: return static_cast<int>(cudaErrorInvalidValue);
   }
   return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace drs
+
+// ------------------------------------------------------------------------------------------------
+// Micro-benchmark (drs_debug_mma_rate): cycles per tcgen05.mma M=128 x N x K=16 issued back to back by one
+// elected thread on operands resident in shared memory (contents irrelevant).
+// ------------------------------------------------------------------------------------------------
+namespace drs {
+
+__global__ void __launch_bounds__(128) mma_rate_kernel(int n, int iters, int unroll4, long long* out) {
+  extern __shared__ uint8_t dyn_smem[];
+  __shared__ __align__(8) uint64_t s_done;
+  __shared__ uint32_t s_tmem_base;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const uint32_t dyn_u32 = smem_u32(dyn_smem);
+  uint8_t* const base = dyn_smem + ((1024u - (dyn_u32 & 1023u)) & 1023u);
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&s_tmem_base, 256);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem_base;
+  if (warp == 1) {
+    const uint32_t a16 = smem_u32(base) >> 4, b16 = smem_u32(base + 16384) >> 4;
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((static_cast<uint32_t>(n) >> 3) << 17) | (8u << 24);
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int i = 0; i < iters; ++i) {
+        if (unroll4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_split(tmem, ((a16 + 2u * k) & 0x3FFFu) | 0x10000u, hi, ((b16 + 2u * k) & 0x3FFFu) | 0x10000u, hi,
+                            idesc, 1u);
+        } else {
+          umma_bf16_split(tmem, (a16 & 0x3FFFu) | 0x10000u, hi, (b16 & 0x3FFFu) | 0x10000u, hi, idesc, 1u);
+        }
+      }
+      umma_commit(&s_done);
+    }
+    __syncwarp();
+    const long long t1 = clock64();
+    mbar_wait(&s_done, 0, nullptr, 0);
+    const long long t2 = clock64();
+    if (threadIdx.x == 32 && blockIdx.x == 0) {
+      out[0] = t1 - t0;  // issue time
+      out[1] = t2 - t0;  // completion time
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+int mma_rate(int n, int iters, int unroll4, int ctas_per_sm, long long* out_host) {
+  long long* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, 16);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  cudaMemset(d, 0, 16);
+  cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  mma_rate_kernel<<<sms * ctas_per_sm, 128, 50 * 1024>>>(n, iters, unroll4, d);
+  e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out_host, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return static_cast<int>(e);
 }
 
 }  // namespace drs

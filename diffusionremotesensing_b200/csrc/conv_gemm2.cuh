@@ -26,17 +26,27 @@ constexpr int kMaxASlots = 8;
 constexpr int kMaxBStages = 8;
 
 struct __align__(16) KBlock2 {
-  uint32_t a_off;     // byte offset of the tap's first pixel inside its A sub-tile
-  uint32_t b_off;     // streamed: byte offset in the global weight blob; resident: byte offset in the smem image
-  uint32_t b_bytes;   // n * ck * 2
-  uint16_t n;         // MMA N
-  uint16_t col;       // accumulator column offset inside one TMEM buffer
-  uint16_t sbo16;     // A descriptor stride between 8-row groups, in 16-byte units
-  uint8_t ck;         // channels of this K-block: 16 / 32 / 64
-  uint8_t flags;      // KB2_*
-  uint32_t pad[3];
+  uint32_t a_off16;    // (byte offset of the tap's first pixel inside its A sub-tile) / 16
+  uint32_t b_off;      // streamed: byte offset in the global weight blob; resident: byte offset in the smem image
+  uint32_t b_bytes;    // n * ck * 2
+  uint32_t desc_hi_a;  // upper half of the A shared-memory descriptor (SBO, version, swizzle mode)
+  uint32_t desc_hi_b;  // upper half of the B descriptor
+  uint32_t idesc;      // tcgen05 instruction descriptor (M = 128, N = n, bf16 x bf16 -> fp32)
+  uint16_t col;        // accumulator column offset inside one TMEM buffer
+  uint8_t nk;          // K = 16 slices in this K-block (ck / 16)
+  uint8_t flags;       // KB2_*
+  uint32_t pad;
 };
 static_assert(sizeof(KBlock2) == 32, "KBlock2 must be 32 bytes");
+
+// Host-side encoders of the descriptor halves the kernel does not need to recompute per K-block.
+inline uint32_t umma_desc_hi(uint32_t row_bytes, uint32_t sbo_bytes) {
+  const uint32_t layout = (row_bytes == 128) ? 2u : (row_bytes == 64) ? 4u : 6u;  // SWIZZLE_128B / 64B / 32B
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+}
+inline uint32_t umma_idesc_host(uint32_t m, uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
 
 enum : uint8_t {
   KB2_INIT = 1,   // first K-block writing these accumulator columns: overwrite
@@ -69,6 +79,7 @@ struct Conv2Args {
   int acc_cols;             // columns one tile's accumulators use
   int acc_bufs;             // 1 or 2
   int n_sub, nsplit;
+  int timeline;             // debug: CTA 0 records clock stamps (DRS_V2_TIMELINE)
   int* err;
   EpiArgs epi;
 };
@@ -76,5 +87,6 @@ struct Conv2Args {
 int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& map1, const Conv2Args& args, int grid,
                       size_t smem_bytes, cudaStream_t stream);
 int conv_gemm2_set_smem_limits();
+int conv_gemm2_read_timeline(long long* host, int n);
 
 }  // namespace drs

@@ -325,12 +325,14 @@ struct Builder {
             for (size_t ti = 0; ti < mine.size(); ++ti) {
               const Tap& tp = *mine[ti];
               KBlock2 kb{};
-              kb.a_off = static_cast<uint32_t>(((tp.dx - G.dx_min) + G.hw * (tp.py + G.npy * (tp.dy - G.dy_min))) * pix);
-              kb.n = static_cast<uint16_t>(n);
+              const int a_off = ((tp.dx - G.dx_min) + G.hw * (tp.py + G.npy * (tp.dy - G.dy_min))) * pix;
+              kb.a_off16 = static_cast<uint32_t>(a_off / 16);
               const int col = (t.col_slot + tp.group) * g.n_sub;
               kb.col = static_cast<uint16_t>(col);
-              kb.sbo16 = static_cast<uint16_t>(G.hw * G.npy * pix / 16);
-              kb.ck = static_cast<uint8_t>(ck);
+              kb.desc_hi_a = umma_desc_hi(pix, G.hw * G.npy * pix);
+              kb.desc_hi_b = umma_desc_hi(pix, 8 * pix);
+              kb.idesc = umma_idesc_host(kTileM, n);
+              kb.nk = static_cast<uint8_t>(ck / 16);
               kb.flags = 0;
               if (seen.insert(col).second) kb.flags |= KB2_INIT;
               if (ti == 0) kb.flags |= KB2_FIRST;

@@ -1,5 +1,6 @@
 // DrsPlan: activation workspace, TMA descriptors, launch list, time tables, sampler, CUDA-graph replay.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -34,7 +35,7 @@ static EncodeTiledFn encode_fn() {
 //   plain view:    (C,  W,   1, H,   B)
 //   stride-2 view: (2C, W/2, 2, H/2, B) -- c = px * C + channel, so a 2x2 / 3x3 stride-2 tap is a plain box
 static int make_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, bool stride2, int ck, int tw,
-                    int th, int tb) {
+                    int th, int tb, int tpy = 1) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -55,7 +56,7 @@ static int make_map(CUtensorMap* map, const void* base, int B, int H, int W, int
     strides[2] = static_cast<cuuint64_t>(2) * W * C * e;
     strides[3] = static_cast<cuuint64_t>(H) * W * C * e;
   }
-  const cuuint32_t box[5] = {static_cast<cuuint32_t>(ck), static_cast<cuuint32_t>(tw), 1u,
+  const cuuint32_t box[5] = {static_cast<cuuint32_t>(ck), static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(tpy),
                              static_cast<cuuint32_t>(th), static_cast<cuuint32_t>(tb)};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUtensorMapSwizzle sw =
@@ -165,6 +166,102 @@ static int bind_launch(DrsPlan* p, int spec_idx, const void* src0, const void* s
   e.bvec = m->f(g.bvec);
   e.nvec = g.nvec;
   return DRS_OK;
+}
+
+// Second-generation binding (conv_gemm2.cuh): used when the output grid holds at least one 8 x 16 tile.
+static int sm_count(int device) {
+  static int n = 0;
+  if (!n) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+  return n > 0 ? n : 148;
+}
+
+static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gridW, int gridH, int srcH[2],
+                          int srcW[2], Launch* L) {
+  const DrsModel* m = p->m;
+  const GemmSpec& g = m->gemms[L->spec];
+  const GemmSpec::V2& v = g.v2;
+  L->use_v2 = false;
+  static const bool disabled = (getenv("DRS_DISABLE_V2") != nullptr);
+  if (disabled || !v.usable || gridH < kTile2H || gridW < kTile2W) return DRS_OK;
+  Conv2Args& a = L->args2;
+  memset(&a, 0, sizeof(a));
+  const void* srcs[2] = {src0, src1};
+  CUtensorMap* maps[2] = {&L->map0, &L->map1};
+  CUtensorMap saved0 = L->map0, saved1 = L->map1;
+  for (int s = 0; s < g.n_src; ++s) {
+    const int r = make_map(maps[s], srcs[s], p->nb, srcH[s], srcW[s], g.src_C[s], g.src_stride2[s] != 0, g.src_ck[s],
+                           v.halo_w[s], v.halo_h[s], 1, v.npy[s]);
+    if (r != DRS_OK) {
+      L->map0 = saved0;
+      L->map1 = saved1;
+      return r;
+    }
+  }
+  if (g.n_src == 1) L->map1 = L->map0;
+  a.kblocks = m->d_kblocks2.as<KBlock2>() + v.kb_dev_off;
+  a.subtiles = m->d_subtiles.as<SubTile>() + v.st_dev_off;
+  a.wpack = m->d_wblob.as<uint8_t>();
+  a.w_split_off = v.w_split_off;
+  a.w_split_bytes = v.w_split_bytes;
+  a.nkb = v.nkb;
+  a.n_sub_tiles = static_cast<int>(v.subtiles.size());
+  a.resident = v.resident ? 1 : 0;
+  a.W = gridW;
+  a.H = gridH;
+  a.B = p->nb;
+  a.tiles_x = (gridW + kTile2W - 1) / kTile2W;
+  a.tiles_y = (gridH + kTile2H - 1) / kTile2H;
+  a.n_tiles = a.tiles_x * a.tiles_y * p->nb;
+  a.a_slot_bytes = v.a_slot_bytes;
+  a.b_stage_bytes = v.b_stage_bytes;
+  a.acc_cols = v.acc_cols;
+  a.acc_bufs = (2 * v.acc_cols <= 512) ? 2 : 1;
+  int alloc = 32;
+  while (alloc < a.acc_bufs * v.acc_cols) alloc <<= 1;
+  a.tmem_cols = alloc;
+  a.n_sub = g.n_sub;
+  a.nsplit = g.nsplit;
+  a.err = p->d_err;
+  static const bool timeline = (getenv("DRS_V2_TIMELINE") != nullptr);
+  a.timeline = timeline ? 1 : 0;
+  a.epi = L->args.epi;
+  // shared memory: weights (resident image or a ring) + as many A slots as useful
+  const int spt = a.n_sub_tiles;
+  a.b_stages = a.resident ? 1 : std::min(4, v.nkb);
+  const int b_bytes = a.resident ? static_cast<int>(v.w_split_bytes) : a.b_stages * v.b_stage_bytes;
+  const int want_slots = std::min(kMaxASlots, std::max(2, 2 * spt));
+  // A single elected thread issues every MMA of a CTA (~100+ cycles per instruction at small N), so several
+  // co-resident CTAs per SM are what keeps the tensor pipe and the epilogue warps busy: take as many as TMEM and
+  // shared memory allow (at most 3), each with at least one tile's sub-tiles plus one slot of prefetch.
+  static const int max_ctas = getenv("DRS_V2_MAX_CTAS") ? atoi(getenv("DRS_V2_MAX_CTAS")) : 3;
+  int ctas = std::min(512 / alloc, max_ctas);
+  int slots = 0;
+  for (; ctas >= 1; --ctas) {
+    const int budget = (227 * 1024) / ctas - 8 * 1024 - b_bytes;
+    slots = std::min(want_slots, budget / v.a_slot_bytes);
+    if (slots >= std::max(2, spt + 1) || ctas == 1) break;
+  }
+  if (slots < 2) return DRS_OK;  // does not fit: stay on the first-generation kernel
+  a.a_slots = slots;
+  L->smem = static_cast<size_t>(slots) * v.a_slot_bytes + b_bytes + 1024;
+  int grid = std::min(a.n_tiles * g.nsplit, sm_count(m->device) * ctas);
+  grid -= grid % g.nsplit;
+  if (grid < g.nsplit) grid = g.nsplit;
+  L->grid2 = grid;
+  L->use_v2 = true;
+  return DRS_OK;
+}
+
+static int launch_one(const DrsPlan* p, const Launch& L, float* eps, cudaStream_t st) {
+  const GemmSpec& g = p->m->gemms[L.spec];
+  if (L.use_v2) {
+    Conv2Args a = L.args2;
+    if (g.epi_kind == EPI_OUT && eps) a.epi.out = eps;
+    return launch_conv_gemm2(g.epi_kind, L.map0, L.map1, a, L.grid2, L.smem, st);
+  }
+  ConvArgs a = L.args;
+  if (g.epi_kind == EPI_OUT && eps) a.epi.out = eps;
+  return launch_conv_gemm(g.epi_kind, L.map0, L.map1, a, L.n_tiles, g.nsplit, L.smem, st);
 }
 
 static int alloc_small(DrsPlan* p) {
@@ -282,6 +379,7 @@ int plan_create(DrsModel* m, int nb, int nx, int ncond, int S, int mag, DrsPlan*
     Launch L;
     DRS_TRY(bind_launch(p.get(), static_cast<int>(gi), src[0], src[1], gridW, gridH, sH, sW, outp, OH, OW, &L));
     if (g.flags & F_ROWSCALE) L.args.epi.psi = reinterpret_cast<const float*>(ws + p->acts.at(g.src_name[1]).offset);
+    DRS_TRY(bind_launch_v2(p.get(), src[0], src[1], gridW, gridH, sH, sW, &L));
     p->launches.push_back(L);
   }
   *out = p.release();
@@ -393,7 +491,10 @@ static int fill_table_rows(DrsPlan* p, float* table, const float* tvals, const i
 }
 
 static void rebind_table(DrsPlan* p) {
-  for (Launch& L : p->launches) L.args.epi.te = p->table.as<float>();
+  for (Launch& L : p->launches) {
+    L.args.epi.te = p->table.as<float>();
+    L.args2.epi.te = p->table.as<float>();
+  }
 }
 
 static void drop_graphs(DrsPlan* p) {
@@ -438,9 +539,7 @@ static int enqueue_forward(DrsPlan* p, const float* x, float* eps, cudaStream_t 
                                                  m->has_cond ? p->ncond : 1, m->desc.x_channels, p->S, st)));
   for (Launch& L : p->launches) {
     const GemmSpec& g = m->gemms[L.spec];
-    ConvArgs a = L.args;
-    if (g.epi_kind == EPI_OUT) a.epi.out = eps;
-    const int r = launch_conv_gemm(g.epi_kind, L.map0, L.map1, a, L.n_tiles, g.nsplit, L.smem, st);
+    const int r = launch_one(p, L, eps, st);
     if (r != 0) {
       set_error("launch of %s failed: %s", g.name.c_str(), cudaGetErrorString(static_cast<cudaError_t>(r)));
       return DRS_E_CUDA;
@@ -627,8 +726,8 @@ int debug_bind_and_run(DrsPlan* p, const void* in, int gridW, int gridH, int src
   int sH[2] = {srcH, 0}, sW[2] = {srcW, 0};
   Launch L;
   DRS_TRY(bind_launch(p, 0, in, nullptr, gridW, gridH, sH, sW, out, OH, OW, &L));
-  const GemmSpec& g = p->m->gemms[0];
-  const int r = launch_conv_gemm(g.epi_kind, L.map0, L.map1, L.args, L.n_tiles, g.nsplit, L.smem, st);
+  DRS_TRY(bind_launch_v2(p, in, nullptr, gridW, gridH, sH, sW, &L));
+  const int r = launch_one(p, L, nullptr, st);
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "launch_conv_gemm(debug)");
   return DRS_OK;
 }
@@ -687,7 +786,7 @@ int launch_info(const DrsPlan* p, int i, char* name, int name_cap, double* flops
       b += grid_px * g.oscale * g.oscale * g.OC * 2;
     *bytes = b;
   }
-  if (ctas) *ctas = L.n_tiles * g.nsplit;
+  if (ctas) *ctas = L.use_v2 ? -L.grid2 : L.n_tiles * g.nsplit;  // negative: persistent second-generation grid
   if (smem_bytes) *smem_bytes = static_cast<int>(L.smem);
   return DRS_OK;
 }
@@ -715,9 +814,7 @@ int plan_profile(DrsPlan* p, const float* x, float* eps, int iters, float* ms_ou
     for (size_t i = 0; i < p->launches.size(); ++i) {
       Launch& L = p->launches[i];
       const GemmSpec& g = m->gemms[L.spec];
-      ConvArgs a = L.args;
-      if (g.epi_kind == EPI_OUT) a.epi.out = eps;
-      const int r = launch_conv_gemm(g.epi_kind, L.map0, L.map1, a, L.n_tiles, g.nsplit, L.smem, st);
+      const int r = launch_one(p, L, eps, st);
       if (r != 0) rc = cuda_fail(static_cast<cudaError_t>(r), g.name.c_str());
       cudaEventRecord(ev[i + 2], st);
     }

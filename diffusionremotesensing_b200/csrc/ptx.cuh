@@ -48,12 +48,29 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  int polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) {  // ~1 s
-      if (err) atomicExch(err, code);
+    // once any role of any CTA has timed out the launch is lost: drain quickly instead of waiting again
+    if (err && (++polls & 63) == 0 && *reinterpret_cast<volatile int*>(err) != 0) return;
+    if (clock64() - t0 > (1ll << 30)) {  // ~0.5 s
+      if (err) atomicCAS(err, 0, code);
       return;
     }
   }
+}
+
+// One lane of a fully converged warp (warp-uniform control flow keeps descriptors in uniform registers).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xFFFFFFFF;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred)::"memory");
+  return pred != 0;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -108,6 +125,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same with both descriptor halves given separately (lower half = (address >> 4) | LBO field).
+__device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed.

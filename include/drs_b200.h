@@ -135,6 +135,16 @@ int drs_debug_conv2d(const float* x_dev, const float* w_host, const float* bias_
                      const float* shift_host, float* y_dev, int B, int Cin, int Cout, int H, int W, int kind, int relu,
                      int device, void* stream);
 
+/* Debug: SM-clock stamps recorded by CTA 0 of the last second-generation convolution launch when the environment
+ * variable DRS_V2_TIMELINE is set (8 values per pixel tile: producer start / last issue, MMA after TMEM-empty wait /
+ * after first A-full wait / after last issue, epilogue after TMEM-full wait / done). n <= 512. */
+int drs_debug_timeline(long long* out_host, int n);
+
+/* Debug micro-benchmark: one elected thread per CTA issues `iters` (x4 if unroll4) back-to-back tcgen05.mma
+ * M=128 x n x K=16 (bf16) on shared-memory operands, `ctas_per_sm` CTAs per SM. out_host[0] = SM cycles until the
+ * last instruction was issued, out_host[1] = cycles until all completed (CTA 0). Synchronises the device. */
+int drs_debug_mma_rate(int n, int iters, int unroll4, int ctas_per_sm, long long* out_host);
+
 /* Intermediate activations of the last forward, converted to fp32 NCHW (tests only). Returns numel written or <0.
  * name: "h0","b0.h","b0.out","d0","b1.out","d1","b2.out","d2","bn.out","g0","psi0","att0","uc0","ut0","x0",... */
 int64_t drs_debug_fetch(DrsPlan* p, const char* name, float* out_dev, int64_t capacity, void* stream);
