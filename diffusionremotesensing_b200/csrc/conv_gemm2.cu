@@ -47,10 +47,8 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sbo(uint32_t smem_addr, uin
 template <int EPI>
 __global__ void __launch_bounds__(kGemm2Threads)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
-                  const Conv2Args a) {
+                  const __grid_constant__ Conv2Args a, const __grid_constant__ Conv2Prog prog) {
   extern __shared__ uint8_t dyn_smem[];
-  __shared__ __align__(16) KBlock2 s_kb[kMaxKBlocks];
-  __shared__ __align__(16) SubTile s_st[kMaxSubTiles];
   __shared__ __align__(8) uint64_t s_afull[kMaxASlots], s_aempty[kMaxASlots];
   __shared__ __align__(8) uint64_t s_bfull[kMaxBStages], s_bempty[kMaxBStages];
   __shared__ __align__(8) uint64_t s_tfull[2], s_tempty[2];
@@ -72,17 +70,10 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   const int oc_off = split * a.n_sub;
   const int nkb = a.nkb;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const uint8_t* const w_image = a.wpack + a.w_split_off + static_cast<size_t>(split) * a.w_split_bytes;
 
   // ---- one-time setup --------------------------------------------------------------------------
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.kblocks + static_cast<size_t>(split) * nkb);
-    uint4* dst = reinterpret_cast<uint4*>(s_kb);
-    for (int i = threadIdx.x; i < nkb * 2; i += kGemm2Threads) dst[i] = __ldg(src + i);
-    const uint4* ssrc = reinterpret_cast<const uint4*>(a.subtiles);
-    uint4* sdst = reinterpret_cast<uint4*>(s_st);
-    for (int i = threadIdx.x; i < a.n_sub_tiles; i += kGemm2Threads) sdst[i] = __ldg(ssrc + i);
-    load_epilogue_params<EPI>(e, a.n_sub, oc_off, s_par, threadIdx.x, kGemm2Threads);
-  }
+  load_epilogue_params<EPI>(e, a.n_sub, oc_off, s_par, threadIdx.x, kGemm2Threads);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map0);
     tma_prefetch_desc(&map1);
@@ -114,10 +105,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     // ---- producer (whole warp walks the program, one elected lane issues) -------------------------
     if (a.resident && elect_one()) {
       mbar_expect_tx(&s_wready, a.w_split_bytes);
-      const uint8_t* src = a.wpack + a.w_split_off + static_cast<size_t>(split) * a.w_split_bytes;
       for (uint32_t off = 0; off < a.w_split_bytes; off += 16384u) {
         const uint32_t n = min(16384u, a.w_split_bytes - off);
-        bulk_load(b_base + off, src + off, n, &s_wready);
+        bulk_load(b_base + off, w_image + off, n, &s_wready);
       }
     }
     __syncwarp();
@@ -131,9 +121,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       int st = 0;
       TL(tno, 0);
       for (int kb = 0; kb < nkb; ++kb) {
-        const uint32_t flags = s_kb[kb].flags;
-        if (flags & KB2_FIRST) {
-          const SubTile T = s_st[st++];
+        const KB3 K = prog.kb[kb];
+        if (K.flags & KB2_FIRST) {
+          const SubTile T = prog.st[st++];
           mbar_wait(&s_aempty[ar.idx], ar.phase ^ 1u, a.err, 1);
           if (elect_one()) {
             mbar_expect_tx(&s_afull[ar.idx], T.bytes);
@@ -144,11 +134,12 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
           ar.advance(a.a_slots);
         }
         if (!a.resident) {
-          const uint32_t b_off = s_kb[kb].b_off, b_bytes = s_kb[kb].b_bytes;
+          const uint32_t b_bytes = prog.b_bytes[K.src];
           mbar_wait(&s_bempty[br.idx], br.phase ^ 1u, a.err, 1);
           if (elect_one()) {
             mbar_expect_tx(&s_bfull[br.idx], b_bytes);
-            bulk_load(b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes, a.wpack + b_off, b_bytes, &s_bfull[br.idx]);
+            bulk_load(b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes, w_image + (static_cast<size_t>(K.b_k) << 10),
+                      b_bytes, &s_bfull[br.idx]);
           }
           __syncwarp();
           br.advance(a.b_stages);
@@ -170,29 +161,37 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       uint32_t slot16 = 0;
       int cur_slot = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const KBlock2 K = s_kb[kb];
+        const KB3 K = prog.kb[kb];
+        bool waited = false;
         if (K.flags & KB2_FIRST) {
           mbar_wait(&s_afull[ar.idx], ar.phase, a.err, 2);
           if (kb == 0) TL(tno, 3);
           cur_slot = ar.idx;
           slot16 = smem_u32(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes) >> 4;
           ar.advance(a.a_slots);
+          waited = true;
         }
         uint32_t sb16;
         if (a.resident) {
-          sb16 = b_base16 + (K.b_off >> 4);
+          sb16 = b_base16 + (static_cast<uint32_t>(K.b_k) << 6);
         } else {
           mbar_wait(&s_bfull[br.idx], br.phase, a.err, 2);
           sb16 = b_base16 + static_cast<uint32_t>((br.idx * a.b_stage_bytes) >> 4);
+          waited = true;
         }
-        tc_fence_after();
+        if (waited) tc_fence_after();
         if (elect_one()) {
+          const uint32_t hi_a = prog.desc_hi_a[K.src], hi_b = prog.desc_hi_b[K.src], idesc = prog.idesc[K.src];
+          const uint32_t nk = prog.nk[K.src];
           const uint32_t a_lo = ((slot16 + K.a_off16) & 0x3FFFu) | 0x10000u;
           const uint32_t b_lo = (sb16 & 0x3FFFu) | 0x10000u;
           const uint32_t d = acc + K.col;
-          umma_bf16_split(d, a_lo, K.desc_hi_a, b_lo, K.desc_hi_b, K.idesc, (K.flags & KB2_INIT) ? 0u : 1u);
-          for (uint32_t k = 1; k < K.nk; ++k)
-            umma_bf16_split(d, a_lo + 2u * k, K.desc_hi_a, b_lo + 2u * k, K.desc_hi_b, K.idesc, 1u);
+          umma_bf16_split(d, a_lo, hi_a, b_lo, hi_b, idesc, (K.flags & KB2_INIT) ? 0u : 1u);
+          if (nk >= 2) umma_bf16_split(d, a_lo + 2u, hi_a, b_lo + 2u, hi_b, idesc, 1u);
+          if (nk == 4) {
+            umma_bf16_split(d, a_lo + 4u, hi_a, b_lo + 4u, hi_b, idesc, 1u);
+            umma_bf16_split(d, a_lo + 6u, hi_a, b_lo + 6u, hi_b, idesc, 1u);
+          }
           if (!a.resident) umma_commit(&s_bempty[br.idx]);
           if (K.flags & KB2_LAST) umma_commit(&s_aempty[cur_slot]);
         }
@@ -256,14 +255,14 @@ int conv_gemm2_read_timeline(long long* host, int n) {
   return static_cast<int>(cudaMemcpyFromSymbol(host, g_timeline, n * sizeof(long long)));
 }
 
-int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& map1, const Conv2Args& args, int grid,
-                      size_t smem_bytes, cudaStream_t stream) {
+int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& map1, const Conv2Args& args,
+                      const Conv2Prog& prog, int grid, size_t smem_bytes, cudaStream_t stream) {
   dim3 g(static_cast<unsigned>(grid), 1, 1);
   dim3 block(kGemm2Threads, 1, 1);
   switch (epi_kind) {
-    case EPI_STD: conv_gemm2_kernel<EPI_STD><<<g, block, smem_bytes, stream>>>(map0, map1, args); break;
-    case EPI_PSI: conv_gemm2_kernel<EPI_PSI><<<g, block, smem_bytes, stream>>>(map0, map1, args); break;
-    case EPI_OUT: conv_gemm2_kernel<EPI_OUT><<<g, block, smem_bytes, stream>>>(map0, map1, args); break;
+    case EPI_STD: conv_gemm2_kernel<EPI_STD><<<g, block, smem_bytes, stream>>>(map0, map1, args, prog); break;
+    case EPI_PSI: conv_gemm2_kernel<EPI_PSI><<<g, block, smem_bytes, stream>>>(map0, map1, args, prog); break;
+    case EPI_OUT: conv_gemm2_kernel<EPI_OUT><<<g, block, smem_bytes, stream>>>(map0, map1, args, prog); break;
     default: return static_cast<int>(cudaErrorInvalidValue);
   }
   return static_cast<int>(cudaGetLastError());
@@ -299,7 +298,13 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int n, int iters, int unr
   tc_fence_after();
   const uint32_t tmem = s_tmem_base;
   if (warp == 1) {
-    const uint32_t a16 = smem_u32(base) >> 4, b16 = smem_u32(base + 16384) >> 4;
+    // unroll4 bit 0: four MMAs (K slices) per iteration; bits 8..23: A group stride in 16-byte units (default 64 =
+    // 1024 B); bits 24..31: A start offset in 128-byte rows
+    const uint32_t sbo16 = ((unroll4 >> 8) & 0xFFFF) ? ((unroll4 >> 8) & 0xFFFF) : 64u;
+    const uint32_t row0 = (unroll4 >> 24) & 0xFF;
+    unroll4 &= 1;
+    const uint32_t a16 = (smem_u32(base) >> 4) + row0 * 8u, b16 = smem_u32(base + 32768) >> 4;
+    const uint32_t hi_a = sbo16 | (1u << 14) | (2u << 29);
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((static_cast<uint32_t>(n) >> 3) << 17) | (8u << 24);
     const long long t0 = clock64();
@@ -308,10 +313,10 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int n, int iters, int unr
         if (unroll4) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_split(tmem, ((a16 + 2u * k) & 0x3FFFu) | 0x10000u, hi, ((b16 + 2u * k) & 0x3FFFu) | 0x10000u, hi,
+            umma_bf16_split(tmem, ((a16 + 2u * k) & 0x3FFFu) | 0x10000u, hi_a, ((b16 + 2u * k) & 0x3FFFu) | 0x10000u, hi,
                             idesc, 1u);
         } else {
-          umma_bf16_split(tmem, (a16 & 0x3FFFu) | 0x10000u, hi, (b16 & 0x3FFFu) | 0x10000u, hi, idesc, 1u);
+          umma_bf16_split(tmem, (a16 & 0x3FFFu) | 0x10000u, hi_a, (b16 & 0x3FFFu) | 0x10000u, hi, idesc, 1u);
         }
       }
       umma_commit(&s_done);

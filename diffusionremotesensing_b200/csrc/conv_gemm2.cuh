@@ -8,7 +8,8 @@
 // with SBO = halo_width * pixel_bytes, so a tap shift (dx, dy) is just start += (dy * halo_width + dx) * pixel_bytes.
 // CTAs are persistent (static round-robin over pixel tiles), keep the layer's weights resident in shared memory when
 // they fit (else stream them through a ring per tile) and double-buffer the TMEM accumulator so the epilogue of tile
-// i overlaps the MMAs of tile i + 1.
+// i overlaps the MMAs of tile i + 1. The K-block program travels as a __grid_constant__ kernel parameter, so the
+// single issuing thread reads it with uniform constant loads (no shared-memory round trip per MMA).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -25,19 +26,40 @@ constexpr int kMaxSubTiles = 16;
 constexpr int kMaxASlots = 8;
 constexpr int kMaxBStages = 8;
 
-struct __align__(16) KBlock2 {
-  uint32_t a_off16;    // (byte offset of the tap's first pixel inside its A sub-tile) / 16
-  uint32_t b_off;      // streamed: byte offset in the global weight blob; resident: byte offset in the smem image
-  uint32_t b_bytes;    // n * ck * 2
-  uint32_t desc_hi_a;  // upper half of the A shared-memory descriptor (SBO, version, swizzle mode)
-  uint32_t desc_hi_b;  // upper half of the B descriptor
-  uint32_t idesc;      // tcgen05 instruction descriptor (M = 128, N = n, bf16 x bf16 -> fp32)
-  uint16_t col;        // accumulator column offset inside one TMEM buffer
-  uint8_t nk;          // K = 16 slices in this K-block (ck / 16)
-  uint8_t flags;       // KB2_*
-  uint32_t pad;
+struct KB3 {          // one K-block = one filter tap of one channel block: nk MMAs of K = 16
+  uint16_t b_k;       // offset of the weight tile inside one split's image, in KiB (tiles are 1 KiB aligned)
+  uint16_t a_off16;   // (byte offset of the tap's first pixel inside its A sub-tile) / 16
+  uint16_t col;       // accumulator column offset inside one TMEM buffer
+  uint8_t flags;      // KB2_*
+  uint8_t src;        // source tensor 0 / 1 (selects the per-source constants)
 };
-static_assert(sizeof(KBlock2) == 32, "KBlock2 must be 32 bytes");
+static_assert(sizeof(KB3) == 8, "KB3 must be 8 bytes");
+
+enum : uint8_t {
+  KB2_INIT = 1,   // first K-block writing these accumulator columns: overwrite
+  KB2_FIRST = 2,  // first K-block of an A sub-tile: acquire the next A slot
+  KB2_LAST = 4,   // last K-block of an A sub-tile: release the slot
+};
+
+struct SubTile {
+  int32_t c;        // coordinate 0 of the TMA box (channel block, plus px * C for stride-2 views)
+  int16_t dx0, dy0; // halo origin relative to the tile origin (coordinates 1 and 3)
+  uint32_t bytes;   // box bytes = ck * 2 * halo_w * npy * halo_h
+  uint8_t src;      // tensor map 0 / 1
+  uint8_t pad[3];
+};
+static_assert(sizeof(SubTile) == 16, "SubTile must be 16 bytes");
+
+struct Conv2Prog {
+  KB3 kb[kMaxKBlocks];
+  SubTile st[kMaxSubTiles];
+  // per-source constants
+  uint32_t desc_hi_a[2];  // upper half of the A shared-memory descriptor (SBO, version, swizzle mode)
+  uint32_t desc_hi_b[2];  // upper half of the B descriptor
+  uint32_t idesc[2];      // tcgen05 instruction descriptor (M = 128, N, bf16 x bf16 -> fp32)
+  uint32_t b_bytes[2];    // weight tile bytes (n * ck * 2)
+  uint32_t nk[2];         // K = 16 slices per K-block (ck / 16)
+};
 
 // Host-side encoders of the descriptor halves the kernel does not need to recompute per K-block.
 inline uint32_t umma_desc_hi(uint32_t row_bytes, uint32_t sbo_bytes) {
@@ -48,29 +70,12 @@ inline uint32_t umma_idesc_host(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
-enum : uint8_t {
-  KB2_INIT = 1,   // first K-block writing these accumulator columns: overwrite
-  KB2_FIRST = 2,  // first K-block of an A sub-tile: acquire the next A slot
-  KB2_LAST = 4,   // last K-block of an A sub-tile: release the slot
-};
-
-struct __align__(16) SubTile {
-  int32_t c;        // coordinate 0 of the TMA box (channel block, plus px * C for stride-2 views)
-  int16_t dx0, dy0; // halo origin relative to the tile origin (coordinates 1 and 3)
-  uint32_t bytes;   // box bytes = ck * 2 * halo_w * npy * halo_h
-  uint8_t src;      // tensor map 0 / 1
-  uint8_t pad[3];
-};
-static_assert(sizeof(SubTile) == 16, "SubTile must be 16 bytes");
-
 struct Conv2Args {
-  const KBlock2* kblocks;   // [nsplit][nkb]
-  const SubTile* subtiles;  // [n_sub_tiles] (same for every split)
-  const uint8_t* wpack;     // weight blob (v2 packing)
-  uint32_t w_split_off;     // resident: byte offset of split 0's image inside wpack
-  uint32_t w_split_bytes;   // resident: bytes of one split's image (multiple of 1024)
+  const uint8_t* wpack;     // weight blob
+  uint32_t w_split_off;     // byte offset of split 0's weight image inside wpack
+  uint32_t w_split_bytes;   // bytes of one split's image (multiple of 1024)
   int nkb, n_sub_tiles;
-  int resident;             // 1: weights loaded once per CTA
+  int resident;             // 1: the split's image is loaded once per CTA, 0: tiles stream through the B ring
   int W, H, B;              // output pixel grid
   int tiles_x, tiles_y, n_tiles;
   int a_slots, a_slot_bytes;
@@ -84,8 +89,8 @@ struct Conv2Args {
   EpiArgs epi;
 };
 
-int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& map1, const Conv2Args& args, int grid,
-                      size_t smem_bytes, cudaStream_t stream);
+int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& map1, const Conv2Args& args,
+                      const Conv2Prog& prog, int grid, size_t smem_bytes, cudaStream_t stream);
 int conv_gemm2_set_smem_limits();
 int conv_gemm2_read_timeline(long long* host, int n);
 

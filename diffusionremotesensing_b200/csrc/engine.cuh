@@ -95,14 +95,12 @@ struct GemmSpec {
   struct V2 {
     bool usable = false;
     bool resident = false;            // weights of one split fit in shared memory
-    int nkb = 0;
-    std::vector<KBlock2> kblocks;     // [nsplit][nkb]
-    std::vector<SubTile> subtiles;
+    int nkb = 0, n_sub_tiles = 0;
+    Conv2Prog prog;                   // K-block / sub-tile program, passed to the kernel by value
     int halo_w[2] = {0, 0}, halo_h[2] = {0, 0}, npy[2] = {1, 1};   // TMA box geometry per source
     int a_slot_bytes = 0, b_stage_bytes = 0;
     int acc_cols = 0;
     uint32_t w_split_off = 0, w_split_bytes = 0;
-    size_t kb_dev_off = 0, st_dev_off = 0;
   } v2;
 };
 
@@ -128,9 +126,7 @@ struct DrsModel {
   std::vector<float> fblob;                      // fp32 parameters (host staging)
   std::vector<uint8_t> wblob;                    // bf16 swizzled weight tiles (host staging)
   std::vector<drs::KBlock> kb_all;
-  std::vector<drs::KBlock2> kb2_all;
-  std::vector<drs::SubTile> st_all;
-  drs::DevMem d_fblob, d_wblob, d_kblocks, d_kblocks2, d_subtiles;
+  drs::DevMem d_fblob, d_wblob, d_kblocks;
   std::vector<drs::GemmSpec> gemms;              // in execution order
   drs::TimeMlp mlps[7];                          // conv_blocks.0-2, bottle_neck, ups.0-2
   int te_stride = 0;
@@ -159,6 +155,7 @@ struct Launch {
   size_t smem = 0;
   bool use_v2 = false;
   Conv2Args args2;
+  const Conv2Prog* prog2 = nullptr;  // points into the model's GemmSpec
   int grid2 = 0;
 };
 

@@ -267,36 +267,47 @@ struct Builder {
         default: return {0, 0, kTile2W + 1, kTile2H + 1, 1};  // CONV_T3x3_S2: taps at (0 / +1)
       }
     };
-    // pass 1: sizes (identical for every split)
+    Conv2Prog& P = v.prog;
+    memset(&P, 0, sizeof(P));
+    // pass 1: sizes and per-source constants (identical for every split)
     size_t w_image = 0;
-    int max_col = 0, max_b = 0, max_a = 0;
+    int max_a = 0, n_kb = 0, n_st = 0;
     for (const ConvTerm& t : terms) {
       const int ck = g.src_ck[t.src];
+      const int pix = ck * 2;
       const Geo G = geo_of(t.kind);
       v.halo_w[t.src] = G.hw;
       v.halo_h[t.src] = G.hh;
       v.npy[t.src] = G.npy;
-      max_a = std::max(max_a, ck * 2 * G.hw * G.hh * G.npy);
+      max_a = std::max(max_a, pix * G.hw * G.hh * G.npy);
       const int n = g.n_sub * static_cast<int>(t.stack.size());
-      const size_t tile_bytes = (static_cast<size_t>(n) * ck * 2 + 1023) & ~static_cast<size_t>(1023);
+      const size_t tile_bytes = (static_cast<size_t>(n) * pix + 1023) & ~static_cast<size_t>(1023);
+      const int n_px = (t.kind == CONV_3x3_S2 || t.kind == CONV_2x2_S2) ? 2 : 1;
       w_image += tile_bytes * taps_of(t.kind).size() * (t.C / ck);
-      max_b = std::max(max_b, n * ck * 2);
+      n_kb += static_cast<int>(taps_of(t.kind).size()) * (t.C / ck);
+      n_st += n_px * (t.C / ck);
+      P.desc_hi_a[t.src] = umma_desc_hi(pix, G.hw * G.npy * pix);
+      P.desc_hi_b[t.src] = umma_desc_hi(pix, 8 * pix);
+      P.idesc[t.src] = umma_idesc_host(kTileM, n);
+      P.b_bytes[t.src] = static_cast<uint32_t>(n * pix);
+      P.nk[t.src] = static_cast<uint32_t>(ck / 16);
     }
+    if (n_kb > kMaxKBlocks || n_st > kMaxSubTiles || (w_image >> 10) > 0xFFFF) return;
     v.a_slot_bytes = (max_a + 1023) & ~1023;
-    v.b_stage_bytes = (max_b + 1023) & ~1023;
+    v.b_stage_bytes = 0;
+    for (int s = 0; s < 2; ++s) v.b_stage_bytes = std::max(v.b_stage_bytes, static_cast<int>((P.b_bytes[s] + 1023) & ~1023u));
     // resident when the split's image plus two A slots leaves a CTA within ~200 KB
     v.resident = (w_image + 2 * static_cast<size_t>(v.a_slot_bytes) <= 200 * 1024);
     v.w_split_bytes = static_cast<uint32_t>(w_image);
     while (m->wblob.size() % 1024) m->wblob.push_back(0);
     v.w_split_off = static_cast<uint32_t>(m->wblob.size());
-    if (v.resident) m->wblob.resize(m->wblob.size() + w_image * g.nsplit);
+    m->wblob.resize(m->wblob.size() + w_image * g.nsplit);
 
-    v.kblocks.clear();
-    v.subtiles.clear();
+    int max_col = 0;
     for (int s = 0; s < g.nsplit; ++s) {
       std::set<int> seen;
-      int count = 0;
-      size_t image_off = 0;  // offset inside this split's resident image
+      int count = 0, st_count = 0;
+      size_t image_off = 0;  // offset inside this split's image (same for every split)
       for (const ConvTerm& t : terms) {
         const int ck = g.src_ck[t.src];
         const int pix = ck * 2;
@@ -314,42 +325,32 @@ struct Builder {
               if (tp.px == px) mine.push_back(&tp);
             if (mine.empty()) continue;
             if (s == 0) {
-              SubTile st{};
+              SubTile& st = P.st[st_count++];
               st.c = px * t.C + c0;
               st.dx0 = static_cast<int16_t>(G.dx_min);
               st.dy0 = static_cast<int16_t>(G.dy_min);
               st.bytes = static_cast<uint32_t>(pix * G.hw * G.hh * G.npy);
               st.src = static_cast<uint8_t>(t.src);
-              v.subtiles.push_back(st);
             }
             for (size_t ti = 0; ti < mine.size(); ++ti) {
               const Tap& tp = *mine[ti];
-              KBlock2 kb{};
               const int a_off = ((tp.dx - G.dx_min) + G.hw * (tp.py + G.npy * (tp.dy - G.dy_min))) * pix;
-              kb.a_off16 = static_cast<uint32_t>(a_off / 16);
               const int col = (t.col_slot + tp.group) * g.n_sub;
-              kb.col = static_cast<uint16_t>(col);
-              kb.desc_hi_a = umma_desc_hi(pix, G.hw * G.npy * pix);
-              kb.desc_hi_b = umma_desc_hi(pix, 8 * pix);
-              kb.idesc = umma_idesc_host(kTileM, n);
-              kb.nk = static_cast<uint8_t>(ck / 16);
-              kb.flags = 0;
-              if (seen.insert(col).second) kb.flags |= KB2_INIT;
-              if (ti == 0) kb.flags |= KB2_FIRST;
-              if (ti + 1 == mine.size()) kb.flags |= KB2_LAST;
+              uint8_t flags = 0;
+              if (seen.insert(col).second) flags |= KB2_INIT;
+              if (ti == 0) flags |= KB2_FIRST;
+              if (ti + 1 == mine.size()) flags |= KB2_LAST;
               max_col = std::max(max_col, col + n);
-              kb.b_bytes = static_cast<uint32_t>(n * pix);
-              uint8_t* tile;
-              if (v.resident) {
-                kb.b_off = static_cast<uint32_t>(image_off);
-                tile = m->wblob.data() + v.w_split_off + static_cast<size_t>(s) * w_image + image_off;
-                image_off += (static_cast<size_t>(kb.b_bytes) + 1023) & ~static_cast<size_t>(1023);
-              } else {
-                while (m->wblob.size() % 128) m->wblob.push_back(0);
-                kb.b_off = static_cast<uint32_t>(m->wblob.size());
-                m->wblob.resize(m->wblob.size() + kb.b_bytes);
-                tile = m->wblob.data() + kb.b_off;
+              if (s == 0) {
+                KB3& kb = P.kb[count];
+                kb.b_k = static_cast<uint16_t>(image_off >> 10);
+                kb.a_off16 = static_cast<uint16_t>(a_off / 16);
+                kb.col = static_cast<uint16_t>(col);
+                kb.flags = flags;
+                kb.src = static_cast<uint8_t>(t.src);
               }
+              uint8_t* tile = m->wblob.data() + v.w_split_off + static_cast<size_t>(s) * w_image + image_off;
+              image_off += (static_cast<size_t>(n) * pix + 1023) & ~static_cast<size_t>(1023);
               for (int r = 0; r < n; ++r) {
                 const WeightRef& wr = t.stack[r / g.n_sub];
                 const int oc = s * g.n_sub + (r % g.n_sub);
@@ -366,20 +367,18 @@ struct Builder {
                   memcpy(tile + o, &h, 2);
                 }
               }
-              v.kblocks.push_back(kb);
               ++count;
             }
           }
         }
       }
-      if (s == 0) v.nkb = count;
+      if (s == 0) {
+        v.nkb = count;
+        v.n_sub_tiles = st_count;
+      }
     }
-    if (v.nkb > kMaxKBlocks || static_cast<int>(v.subtiles.size()) > kMaxSubTiles || max_col > 512) return;
+    if (max_col > 512) return;
     v.acc_cols = max_col;
-    v.kb_dev_off = m->kb2_all.size();
-    m->kb2_all.insert(m->kb2_all.end(), v.kblocks.begin(), v.kblocks.end());
-    v.st_dev_off = m->st_all.size();
-    m->st_all.insert(m->st_all.end(), v.subtiles.begin(), v.subtiles.end());
     v.usable = true;
   }
 };
@@ -778,8 +777,6 @@ int model_create(const DrsModelDesc* desc, const DrsTensor* tensors, int n_tenso
   DRS_TRY(m->d_fblob.upload(m->fblob.data(), m->fblob.size() * sizeof(float)));
   DRS_TRY(m->d_wblob.upload(m->wblob.data(), m->wblob.size()));
   DRS_TRY(m->d_kblocks.upload(m->kb_all.data(), m->kb_all.size() * sizeof(KBlock)));
-  DRS_TRY(m->d_kblocks2.upload(m->kb2_all.data(), m->kb2_all.size() * sizeof(KBlock2)));
-  DRS_TRY(m->d_subtiles.upload(m->st_all.data(), m->st_all.size() * sizeof(SubTile)));
   int r = conv_gemm_set_smem_limits();
   if (r == 0) r = conv_gemm2_set_smem_limits();
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "cudaFuncSetAttribute(conv_gemm_kernel)");
@@ -824,8 +821,6 @@ int build_debug_conv(DrsModel* m, const float* w, const float* bias, const float
   DRS_TRY(m->d_fblob.upload(m->fblob.data(), m->fblob.size() * sizeof(float)));
   DRS_TRY(m->d_wblob.upload(m->wblob.data(), m->wblob.size()));
   DRS_TRY(m->d_kblocks.upload(m->kb_all.data(), m->kb_all.size() * sizeof(KBlock)));
-  DRS_TRY(m->d_kblocks2.upload(m->kb2_all.data(), m->kb2_all.size() * sizeof(KBlock2)));
-  DRS_TRY(m->d_subtiles.upload(m->st_all.data(), m->st_all.size() * sizeof(SubTile)));
   int r = conv_gemm_set_smem_limits();
   if (r == 0) r = conv_gemm2_set_smem_limits();
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "cudaFuncSetAttribute(conv_gemm_kernel)");

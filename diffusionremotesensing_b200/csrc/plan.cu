@@ -198,13 +198,12 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
     }
   }
   if (g.n_src == 1) L->map1 = L->map0;
-  a.kblocks = m->d_kblocks2.as<KBlock2>() + v.kb_dev_off;
-  a.subtiles = m->d_subtiles.as<SubTile>() + v.st_dev_off;
+  L->prog2 = &v.prog;
   a.wpack = m->d_wblob.as<uint8_t>();
   a.w_split_off = v.w_split_off;
   a.w_split_bytes = v.w_split_bytes;
   a.nkb = v.nkb;
-  a.n_sub_tiles = static_cast<int>(v.subtiles.size());
+  a.n_sub_tiles = v.n_sub_tiles;
   a.resident = v.resident ? 1 : 0;
   a.W = gridW;
   a.H = gridH;
@@ -257,7 +256,7 @@ static int launch_one(const DrsPlan* p, const Launch& L, float* eps, cudaStream_
   if (L.use_v2) {
     Conv2Args a = L.args2;
     if (g.epi_kind == EPI_OUT && eps) a.epi.out = eps;
-    return launch_conv_gemm2(g.epi_kind, L.map0, L.map1, a, L.grid2, L.smem, st);
+    return launch_conv_gemm2(g.epi_kind, L.map0, L.map1, a, *L.prog2, L.grid2, L.smem, st);
   }
   ConvArgs a = L.args;
   if (g.epi_kind == EPI_OUT && eps) a.epi.out = eps;
