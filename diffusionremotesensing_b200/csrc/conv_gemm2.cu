@@ -134,12 +134,11 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
           ar.advance(a.a_slots);
         }
         if (!a.resident) {
-          const uint32_t b_bytes = prog.b_bytes[K.src];
           mbar_wait(&s_bempty[br.idx], br.phase ^ 1u, a.err, 1);
           if (elect_one()) {
-            mbar_expect_tx(&s_bfull[br.idx], b_bytes);
-            bulk_load(b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes, w_image + (static_cast<size_t>(K.b_k) << 10),
-                      b_bytes, &s_bfull[br.idx]);
+            mbar_expect_tx(&s_bfull[br.idx], K.b_bytes);
+            bulk_load(b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes, w_image + K.b_off, K.b_bytes,
+                      &s_bfull[br.idx]);
           }
           __syncwarp();
           br.advance(a.b_stages);
@@ -158,45 +157,51 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       tc_fence_after();
       TL(tno, 2);
       const uint32_t acc = tmem + static_cast<uint32_t>(tr.idx * a.acc_cols);
-      uint32_t slot16 = 0;
-      int cur_slot = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const KB3 K = prog.kb[kb];
-        bool waited = false;
-        if (K.flags & KB2_FIRST) {
-          mbar_wait(&s_afull[ar.idx], ar.phase, a.err, 2);
-          if (kb == 0) TL(tno, 3);
-          cur_slot = ar.idx;
-          slot16 = smem_u32(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes) >> 4;
-          ar.advance(a.a_slots);
-          waited = true;
-        }
-        uint32_t sb16;
-        if (a.resident) {
-          sb16 = b_base16 + (static_cast<uint32_t>(K.b_k) << 6);
-        } else {
-          mbar_wait(&s_bfull[br.idx], br.phase, a.err, 2);
-          sb16 = b_base16 + static_cast<uint32_t>((br.idx * a.b_stage_bytes) >> 4);
-          waited = true;
-        }
-        if (waited) tc_fence_after();
-        if (elect_one()) {
-          const uint32_t hi_a = prog.desc_hi_a[K.src], hi_b = prog.desc_hi_b[K.src], idesc = prog.idesc[K.src];
-          const uint32_t nk = prog.nk[K.src];
-          const uint32_t a_lo = ((slot16 + K.a_off16) & 0x3FFFu) | 0x10000u;
-          const uint32_t b_lo = (sb16 & 0x3FFFu) | 0x10000u;
-          const uint32_t d = acc + K.col;
-          umma_bf16_split(d, a_lo, hi_a, b_lo, hi_b, idesc, (K.flags & KB2_INIT) ? 0u : 1u);
-          if (nk >= 2) umma_bf16_split(d, a_lo + 2u, hi_a, b_lo + 2u, hi_b, idesc, 1u);
-          if (nk == 4) {
-            umma_bf16_split(d, a_lo + 4u, hi_a, b_lo + 4u, hi_b, idesc, 1u);
-            umma_bf16_split(d, a_lo + 6u, hi_a, b_lo + 6u, hi_b, idesc, 1u);
+      // One warp-level step per A sub-tile: the warp waits for the tile, then one elected lane issues every MMA
+      // of every tap that reads it back to back (resident weights need no further waits; streamed weights are
+      // waited for by the issuing lane itself).
+      int kb = 0;
+      while (kb < nkb) {
+        mbar_wait(&s_afull[ar.idx], ar.phase, a.err, 2);
+        tc_fence_after();
+        if (kb == 0) TL(tno, 3);
+        const uint32_t slot16 = smem_u32(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes) >> 4;
+        int kb_end = kb;
+        const bool leader = elect_one();
+        if (leader) {
+          for (;;) {
+            const KB3 K = prog.kb[kb_end];
+            uint32_t b_lo;
+            if (a.resident) {
+              b_lo = K.b_lo + b_base16;
+            } else {
+              mbar_wait(&s_bfull[br.idx], br.phase, a.err, 2);
+              tc_fence_after();
+              b_lo = 0x10000u + b_base16 + static_cast<uint32_t>((br.idx * a.b_stage_bytes) >> 4);
+            }
+            const uint32_t a_lo = K.a_lo + slot16;
+            const uint32_t d = acc + K.col;
+            umma_bf16_split(d, a_lo, K.a_hi, b_lo, K.b_hi, K.idesc, (K.flags & KB2_INIT) ? 0u : 1u);
+            if (K.nk >= 2) umma_bf16_split(d, a_lo + 2u, K.a_hi, b_lo + 2u, K.b_hi, K.idesc, 1u);
+            if (K.nk == 4) {
+              umma_bf16_split(d, a_lo + 4u, K.a_hi, b_lo + 4u, K.b_hi, K.idesc, 1u);
+              umma_bf16_split(d, a_lo + 6u, K.a_hi, b_lo + 6u, K.b_hi, K.idesc, 1u);
+            }
+            if (!a.resident) {
+              umma_commit(&s_bempty[br.idx]);
+              br.advance(a.b_stages);
+            }
+            ++kb_end;
+            if (K.flags & KB2_LAST) break;
           }
-          if (!a.resident) umma_commit(&s_bempty[br.idx]);
-          if (K.flags & KB2_LAST) umma_commit(&s_aempty[cur_slot]);
+          umma_commit(&s_aempty[ar.idx]);
         }
-        __syncwarp();
-        if (!a.resident) br.advance(a.b_stages);
+        // every lane learns how far the elected lane went; ring positions are warp-uniform state
+        kb_end = __reduce_max_sync(0xffffffffu, kb_end);
+        if (!a.resident && !leader)
+          for (int i = kb; i < kb_end; ++i) br.advance(a.b_stages);
+        kb = kb_end;
+        ar.advance(a.a_slots);
       }
       if (elect_one()) umma_commit(&s_tfull[tr.idx]);
       __syncwarp();

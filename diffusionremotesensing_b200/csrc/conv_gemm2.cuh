@@ -26,14 +26,19 @@ constexpr int kMaxSubTiles = 16;
 constexpr int kMaxASlots = 8;
 constexpr int kMaxBStages = 8;
 
-struct KB3 {          // one K-block = one filter tap of one channel block: nk MMAs of K = 16
-  uint16_t b_k;       // offset of the weight tile inside one split's image, in KiB (tiles are 1 KiB aligned)
-  uint16_t a_off16;   // (byte offset of the tap's first pixel inside its A sub-tile) / 16
+struct __align__(16) KB3 {  // one K-block = one filter tap of one channel block: nk MMAs of K = 16
+  uint32_t a_lo;      // lower half of the A descriptor relative to the A slot: (tap offset / 16) | LBO field
+  uint32_t a_hi;      // upper half of the A descriptor (SBO = halo row pitch, version, swizzle mode)
+  uint32_t b_lo;      // lower half of the B descriptor relative to the weight region: (tile offset / 16) | LBO field
+  uint32_t b_hi;      // upper half of the B descriptor
+  uint32_t idesc;     // tcgen05 instruction descriptor (M = 128, N, bf16 x bf16 -> fp32)
   uint16_t col;       // accumulator column offset inside one TMEM buffer
+  uint8_t nk;         // K = 16 slices (ck / 16)
   uint8_t flags;      // KB2_*
-  uint8_t src;        // source tensor 0 / 1 (selects the per-source constants)
+  uint32_t b_off;     // byte offset of the weight tile inside one split's image (tiles are 1 KiB aligned)
+  uint32_t b_bytes;   // weight tile bytes (n * ck * 2)
 };
-static_assert(sizeof(KB3) == 8, "KB3 must be 8 bytes");
+static_assert(sizeof(KB3) == 32, "KB3 must be 32 bytes");
 
 enum : uint8_t {
   KB2_INIT = 1,   // first K-block writing these accumulator columns: overwrite
@@ -53,12 +58,6 @@ static_assert(sizeof(SubTile) == 16, "SubTile must be 16 bytes");
 struct Conv2Prog {
   KB3 kb[kMaxKBlocks];
   SubTile st[kMaxSubTiles];
-  // per-source constants
-  uint32_t desc_hi_a[2];  // upper half of the A shared-memory descriptor (SBO, version, swizzle mode)
-  uint32_t desc_hi_b[2];  // upper half of the B descriptor
-  uint32_t idesc[2];      // tcgen05 instruction descriptor (M = 128, N, bf16 x bf16 -> fp32)
-  uint32_t b_bytes[2];    // weight tile bytes (n * ck * 2)
-  uint32_t nk[2];         // K = 16 slices per K-block (ck / 16)
 };
 
 // Host-side encoders of the descriptor halves the kernel does not need to recompute per K-block.

@@ -271,7 +271,7 @@ struct Builder {
     memset(&P, 0, sizeof(P));
     // pass 1: sizes and per-source constants (identical for every split)
     size_t w_image = 0;
-    int max_a = 0, n_kb = 0, n_st = 0;
+    int max_a = 0, max_b = 0, n_kb = 0, n_st = 0;
     for (const ConvTerm& t : terms) {
       const int ck = g.src_ck[t.src];
       const int pix = ck * 2;
@@ -286,16 +286,11 @@ struct Builder {
       w_image += tile_bytes * taps_of(t.kind).size() * (t.C / ck);
       n_kb += static_cast<int>(taps_of(t.kind).size()) * (t.C / ck);
       n_st += n_px * (t.C / ck);
-      P.desc_hi_a[t.src] = umma_desc_hi(pix, G.hw * G.npy * pix);
-      P.desc_hi_b[t.src] = umma_desc_hi(pix, 8 * pix);
-      P.idesc[t.src] = umma_idesc_host(kTileM, n);
-      P.b_bytes[t.src] = static_cast<uint32_t>(n * pix);
-      P.nk[t.src] = static_cast<uint32_t>(ck / 16);
+      max_b = std::max(max_b, n * pix);
     }
-    if (n_kb > kMaxKBlocks || n_st > kMaxSubTiles || (w_image >> 10) > 0xFFFF) return;
+    if (n_kb > kMaxKBlocks || n_st > kMaxSubTiles) return;
     v.a_slot_bytes = (max_a + 1023) & ~1023;
-    v.b_stage_bytes = 0;
-    for (int s = 0; s < 2; ++s) v.b_stage_bytes = std::max(v.b_stage_bytes, static_cast<int>((P.b_bytes[s] + 1023) & ~1023u));
+    v.b_stage_bytes = (max_b + 1023) & ~1023;
     // resident when the split's image plus two A slots leaves a CTA within ~200 KB
     v.resident = (w_image + 2 * static_cast<size_t>(v.a_slot_bytes) <= 200 * 1024);
     v.w_split_bytes = static_cast<uint32_t>(w_image);
@@ -343,11 +338,16 @@ struct Builder {
               max_col = std::max(max_col, col + n);
               if (s == 0) {
                 KB3& kb = P.kb[count];
-                kb.b_k = static_cast<uint16_t>(image_off >> 10);
-                kb.a_off16 = static_cast<uint16_t>(a_off / 16);
+                kb.a_lo = static_cast<uint32_t>(a_off / 16) | 0x10000u;
+                kb.a_hi = umma_desc_hi(pix, G.hw * G.npy * pix);
+                kb.b_lo = static_cast<uint32_t>(image_off / 16) | 0x10000u;
+                kb.b_hi = umma_desc_hi(pix, 8 * pix);
+                kb.idesc = umma_idesc_host(kTileM, n);
                 kb.col = static_cast<uint16_t>(col);
+                kb.nk = static_cast<uint8_t>(ck / 16);
                 kb.flags = flags;
-                kb.src = static_cast<uint8_t>(t.src);
+                kb.b_off = static_cast<uint32_t>(image_off);
+                kb.b_bytes = static_cast<uint32_t>(n * pix);
               }
               uint8_t* tile = m->wblob.data() + v.w_split_off + static_cast<size_t>(s) * w_image + image_off;
               image_off += (static_cast<size_t>(n) * pix + 1023) & ~static_cast<size_t>(1023);
