@@ -221,8 +221,8 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   a.n_sub = g.n_sub;
   a.nsplit = g.nsplit;
   a.err = p->d_err;
-  static const bool timeline = (getenv("DRS_V2_TIMELINE") != nullptr);
-  a.timeline = timeline ? 1 : 0;
+  static const int timeline = getenv("DRS_V2_TIMELINE") ? atoi(getenv("DRS_V2_TIMELINE")) : 0;
+  a.timeline = timeline;  // bit 0: record stamps, bit 1: skip the epilogue body (timing experiments only)
   a.epi = L->args.epi;
   // shared memory: weights (resident image or a ring) + as many A slots as useful
   const int spt = a.n_sub_tiles;

@@ -142,6 +142,19 @@ __device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, 
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Adds to the lower 32 bits of a shared-memory descriptor (start-address field; callers guarantee no carry).
+__device__ __forceinline__ uint64_t desc_add_lo(uint64_t d, uint32_t x) {
+  uint64_t r;
+  asm("{\n"
+      ".reg .b32 lo, hi;\n"
+      "mov.b64 {lo, hi}, %1;\n"
+      "add.u32 lo, lo, %2;\n"
+      "mov.b64 %0, {lo, hi};\n"
+      "}\n"
+      : "=l"(r)
+      : "l"(d), "r"(x));
+  return r;
+}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -22,7 +22,4 @@ names = ["p_start", "p_issued", "m_tmemfree", "m_afull", "m_issued", "e_tfull", 
 print("tile " + " ".join(f"{n:>11s}" for n in names))
 for t in range(12):
     print(f"{t:4d} " + " ".join(f"{buf[t * 8 + s] - t0:11d}" for s in range(7)))
-print("per-K-block stamps of tile 3 (MMA thread): start, after fence, after MMAs, after commit")
-base = buf[256]
-for kb in range(12):
-    print(kb, [buf[256 + 4 * kb + j] - base for j in range(4)])
+print("K-block start stamps of tile 3 (issuing lane):", [buf[256 + kb] - buf[256] for kb in range(20) if buf[256 + kb] > 0])
