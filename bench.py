@@ -247,6 +247,7 @@ def run_ours(args):
         n_l = lib.drs_plan_launch_count(plan)
         ms_out = torch.zeros(n_l, dtype=torch.float32)
         N.check(lib.drs_plan_profile(plan, N.ptr(x), N.ptr(eps), max(3, min(K, 10)), N.ptr(ms_out), st))
+        N.check(lib.drs_plan_check(plan, st))
         tot_f = tot_ms = 0.0
         for i in range(n_l):
             name = C.create_string_buffer(64)

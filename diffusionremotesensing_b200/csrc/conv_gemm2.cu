@@ -1,11 +1,18 @@
 // Persistent halo-tile tcgen05 convolution kernel (see conv_gemm2.cuh for the model).
 //
-// CTA = 192 threads, one CTA (or two, when shared memory and TMEM allow) per SM, looping over pixel tiles:
-//   warp 0 (one lane)  producer: resident weights once; per tile one 5-D TMA box per A sub-tile (halo tile of one
-//                      channel block) and, when the weights are streamed, one bulk copy per K-block
-//   warp 1 (one lane)  tcgen05.mma issuer; owns the TMEM allocation (1 or 2 accumulator buffers)
-//   warps 2..5         epilogue of the previous tile (tcgen05.ld, fused affine / ReLU / adds, global stores)
-// Rings: A slots (full/empty), B stages (full/empty, streamed mode), TMEM buffers (full/empty).
+// CTA = 352 threads, persistent, looping over PAIRS of pixel tiles. A single thread can issue a tcgen05.mma only
+// every ~85 cycles in this loop while the tensor pipe needs 40-64 cycles for the small-N MMAs of this network, so one
+// CTA runs two MMA issuers and two epilogue groups, one per tile of the pair and per TMEM accumulator buffer; both
+// issuers walk the same K-block program in step, so a streamed weight tile is fetched once per pair.
+//   warps 0..3   epilogue of tile 0 of the pair (tcgen05.ld, fused affine / ReLU / adds, global stores)
+//   warps 4..7   epilogue of tile 1
+//   warp 8, 9    tcgen05.mma issuers of tile 0 / tile 1 (one elected lane each); warp 8 owns the TMEM allocation
+//   warp 10      producer: resident weights once; per tile one 5-D TMA box per A sub-tile (halo tile of one channel
+//                block) and, when the weights are streamed, one bulk copy per K-block and pair
+// The single-lane roles have the highest warp ids: the sub-partition arbiter favours the highest id among eligible
+// warps, so spinning or ALU-heavy epilogue warps never starve the issuer they wait for.
+// Rings: A slots (full/empty, filled in the order (sub-tile, tile-of-pair)), B stages (full / empty-by-both-issuers,
+// streamed mode), TMEM buffer p (full/empty) for tile p of the pair.
 #include <string.h>
 
 #include "conv_epilogue.cuh"
@@ -14,13 +21,13 @@
 
 namespace drs {
 
-// Debug timeline (DRS_V2_TIMELINE=1): CTA 0 records SM-clock stamps of its first tiles, 8 slots per tile:
-// 0 producer tile start, 1 producer last issue, 2 MMA after tmem-empty wait, 3 MMA after first A-full wait,
-// 4 MMA after last issue, 5 epilogue after tmem-full wait, 6 epilogue done.
+// Debug timeline (DRS_V2_TIMELINE=1): CTA 0 records SM-clock stamps of its first tile pairs, 8 slots per pair:
+// 0 producer pair start, 1 producer last issue, 2 MMA(0) after tmem-empty wait, 3 MMA(0) after first A-full wait,
+// 4 MMA(0) after last issue, 5 epilogue(0) after tmem-full wait, 6 epilogue(0) done, 7 MMA(1) after last issue.
 __device__ long long g_timeline[64 * 8];
 #define TL(tile_no, slot)                                                                       \
   do {                                                                                          \
-    if (a.timeline && blockIdx.x == 0 && (tile_no) < 64) g_timeline[(tile_no) * 8 + (slot)] = clock64(); \
+    if ((a.timeline & 1) && blockIdx.x == 0 && (tile_no) < 64) g_timeline[(tile_no) * 8 + (slot)] = clock64(); \
   } while (0)
 
 struct RingPos {
@@ -34,24 +41,8 @@ struct RingPos {
   }
 };
 
-// K-major swizzled operand whose 8-row groups are `sbo16 * 16` bytes apart (rows inside a group: row_bytes apart).
-__device__ __forceinline__ uint64_t umma_desc_kmajor_sbo(uint32_t smem_addr, uint32_t row_bytes, uint32_t sbo16) {
-  const uint64_t layout = (row_bytes == 128) ? 2ull : (row_bytes == 64) ? 4ull : 6ull;
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= 1ull << 16;
-  d |= static_cast<uint64_t>(sbo16 & 0x3FFF) << 32;
-  d |= 1ull << 46;
-  d |= layout << 61;
-  return d;
-}
-
-// Warp roles. The SM sub-partition arbiter favours the highest warp id among eligible warps, so the two
-// single-lane roles sit on the highest ids (sharing sub-partitions 0 and 1 with epilogue warps 0 and 1): a spinning
-// or ALU-heavy epilogue warp then cannot starve the MMA issuer it is waiting for. Epilogue warp w reads TMEM lane
-// quadrant w.
-constexpr int kMmaWarp = 4;
-constexpr int kProducerWarp = 5;
+constexpr int kMmaWarp0 = 8;      // issuer of tile 0 of a pair (tile 1: kMmaWarp0 + 1)
+constexpr int kProducerWarp = 10;
 
 template <int EPI>
 __global__ void __launch_bounds__(kGemm2Threads)
@@ -92,7 +83,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     }
     for (int s = 0; s < a.b_stages; ++s) {
       mbar_init(&s_bfull[s], 1);
-      mbar_init(&s_bempty[s], 1);
+      mbar_init(&s_bempty[s], 2);  // released by both issuers
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_tfull[s], 1);
@@ -101,7 +92,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     mbar_init(&s_wready, 1);
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) {
+  if (warp == kMmaWarp0) {
     tmem_alloc(&s_tmem_base, static_cast<uint32_t>(a.tmem_cols));
     tmem_relinquish();
   }
@@ -121,26 +112,38 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     }
     __syncwarp();
     RingPos ar{0, 0}, br{0, 0};
-    int tno = 0;
-    for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++tno) {
-      const int b = tile / tiles_per_img;
-      const int t2 = tile - b * tiles_per_img;
-      const int y0 = (t2 / a.tiles_x) * kTile2H;
-      const int x0 = (t2 % a.tiles_x) * kTile2W;
+    int pno = 0;
+    for (int tile0 = first_tile; tile0 < a.n_tiles; tile0 += 2 * tile_step, ++pno) {
+      int x0[2], y0[2], bb[2];
+      bool valid[2];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int tile = tile0 + p * tile_step;
+        valid[p] = tile < a.n_tiles;
+        bb[p] = tile / tiles_per_img;
+        const int t2 = tile - bb[p] * tiles_per_img;
+        y0[p] = (t2 / a.tiles_x) * kTile2H;
+        x0[p] = (t2 % a.tiles_x) * kTile2W;
+      }
       int st = 0;
-      TL(tno, 0);
+      TL(pno, 0);
       for (int kb = 0; kb < nkb; ++kb) {
         const KB3 K = prog.kb[kb];
         if (K.flags & KB2_FIRST) {
           const SubTile T = prog.st[st++];
-          mbar_wait(&s_aempty[ar.idx], ar.phase ^ 1u, a.err, 1);
-          if (elect_one()) {
-            mbar_expect_tx(&s_afull[ar.idx], T.bytes);
-            tma_load_5d(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes, T.src ? &map1 : &map0, &s_afull[ar.idx],
-                        T.c, x0 + T.dx0, 0, y0 + T.dy0, b);
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            if (valid[p]) {
+              mbar_wait(&s_aempty[ar.idx], ar.phase ^ 1u, a.err, 1);
+              if (elect_one()) {
+                mbar_expect_tx(&s_afull[ar.idx], T.bytes);
+                tma_load_5d(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes, T.src ? &map1 : &map0,
+                            &s_afull[ar.idx], T.c, x0[p] + T.dx0, 0, y0[p] + T.dy0, bb[p]);
+              }
+              __syncwarp();
+            }
+            ar.advance(a.a_slots);  // the slot sequence is (sub-tile, tile-of-pair) whether or not tile 1 exists
           }
-          __syncwarp();
-          ar.advance(a.a_slots);
         }
         if (!a.resident) {
           mbar_wait(&s_bempty[br.idx], br.phase ^ 1u, a.err, 1);
@@ -153,27 +156,34 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
           br.advance(a.b_stages);
         }
       }
-      TL(tno, 1);
+      TL(pno, 1);
     }
-  } else if (warp == kMmaWarp) {
-    // ---- MMA issuer (whole warp walks the program, one elected lane issues) -----------------------
+  } else if (warp == kMmaWarp0 || warp == kMmaWarp0 + 1) {
+    // ---- MMA issuer of tile p of every pair ------------------------------------------------------------
+    const int p = warp - kMmaWarp0;
     if (a.resident) mbar_wait(&s_wready, 0, a.err, 2);
-    RingPos ar{0, 0}, br{0, 0}, tr{0, 0};
+    RingPos ar{0, 0}, br{0, 0};
+    if (p) ar.advance(a.a_slots);
     const uint32_t b_base16 = smem_u32(b_base) >> 4;
-    int tno = 0;
-    for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++tno) {
-      mbar_wait(&s_tempty[tr.idx], tr.phase ^ 1u, a.err, 2);
-      tc_fence_after();
-      TL(tno, 2);
-      const uint32_t acc = tmem + static_cast<uint32_t>(tr.idx * a.acc_cols);
-      // One warp-level step per A sub-tile: the warp waits for the tile, then one elected lane issues every MMA
-      // of every tap that reads it back to back (resident weights need no further waits; streamed weights are
-      // waited for by the issuing lane itself).
+    const uint32_t acc = tmem + static_cast<uint32_t>(p * a.acc_cols);
+    uint32_t tphase = 0;
+    int pno = 0;
+    for (int tile0 = first_tile; tile0 < a.n_tiles; tile0 += 2 * tile_step, ++pno) {
+      const bool valid = (tile0 + p * tile_step) < a.n_tiles;
+      if (valid) {
+        mbar_wait(&s_tempty[p], tphase ^ 1u, a.err, 2);
+        tc_fence_after();
+      }
+      if (p == 0) TL(pno, 2);
+      // One warp-level step per A sub-tile: the warp waits for its halo tile, then one elected lane issues every
+      // MMA of every tap that reads it back to back (streamed weights are waited for by the issuing lane itself).
       int kb = 0;
       while (kb < nkb) {
-        mbar_wait(&s_afull[ar.idx], ar.phase, a.err, 2);
-        tc_fence_after();
-        if (kb == 0) TL(tno, 3);
+        if (valid) {
+          mbar_wait(&s_afull[ar.idx], ar.phase, a.err, 2);
+          tc_fence_after();
+        }
+        if (p == 0 && kb == 0) TL(pno, 3);
         const uint32_t slot16 = smem_u32(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes) >> 4;
         int kb_end = kb;
         const bool leader = elect_one();
@@ -188,22 +198,27 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
               tc_fence_after();
               b_lo = 0x10000u + b_base16 + static_cast<uint32_t>((br.idx * a.b_stage_bytes) >> 4);
             }
-            const uint32_t a_lo = K.a_lo + slot16;
-            const uint32_t d = acc + K.col;
-            umma_bf16_split(d, a_lo, K.a_hi, b_lo, K.b_hi, K.idesc, (K.flags & KB2_INIT) ? 0u : 1u);
-            if (K.nk >= 2) umma_bf16_split(d, a_lo + 2u, K.a_hi, b_lo + 2u, K.b_hi, K.idesc, 1u);
-            if (K.nk == 4) {
-              umma_bf16_split(d, a_lo + 4u, K.a_hi, b_lo + 4u, K.b_hi, K.idesc, 1u);
-              umma_bf16_split(d, a_lo + 6u, K.a_hi, b_lo + 6u, K.b_hi, K.idesc, 1u);
+            if (valid) {
+              const uint32_t a_lo = K.a_lo + slot16;
+              const uint32_t d = acc + K.col;
+              umma_bf16_split(d, a_lo, K.a_hi, b_lo, K.b_hi, K.idesc, (K.flags & KB2_INIT) ? 0u : 1u);
+              if (K.nk >= 2) umma_bf16_split(d, a_lo + 2u, K.a_hi, b_lo + 2u, K.b_hi, K.idesc, 1u);
+              if (K.nk == 4) {
+                umma_bf16_split(d, a_lo + 4u, K.a_hi, b_lo + 4u, K.b_hi, K.idesc, 1u);
+                umma_bf16_split(d, a_lo + 6u, K.a_hi, b_lo + 6u, K.b_hi, K.idesc, 1u);
+              }
             }
             if (!a.resident) {
-              umma_commit(&s_bempty[br.idx]);
+              if (valid)
+                umma_commit(&s_bempty[br.idx]);
+              else
+                mbar_arrive(&s_bempty[br.idx]);  // no tile 1 in the last pair: release the stage unused
               br.advance(a.b_stages);
             }
             ++kb_end;
             if (K.flags & KB2_LAST) break;
           }
-          umma_commit(&s_aempty[ar.idx]);
+          if (valid) umma_commit(&s_aempty[ar.idx]);
         }
         // every lane learns how far the elected lane went; ring positions are warp-uniform state
         kb_end = __reduce_max_sync(0xffffffffu, kb_end);
@@ -211,42 +226,46 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
           for (int i = kb; i < kb_end; ++i) br.advance(a.b_stages);
         kb = kb_end;
         ar.advance(a.a_slots);
+        ar.advance(a.a_slots);
       }
-      if (elect_one()) umma_commit(&s_tfull[tr.idx]);
+      if (valid && elect_one()) umma_commit(&s_tfull[p]);
       __syncwarp();
-      TL(tno, 4);
-      tr.advance(a.acc_bufs);
+      TL(pno, p ? 7 : 4);
+      tphase ^= 1u;
     }
   } else {
-    // ---- epilogue ------------------------------------------------------------------------------
+    // ---- epilogue group p: tile p of every pair ----------------------------------------------------------
+    const int p = warp >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int lx = row & (kTile2W - 1);
     const int ly = row >> 3;
-    RingPos tr{0, 0};
-    int tno = 0;
-    for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++tno) {
+    uint32_t tphase = 0;
+    int pno = 0;
+    for (int tile0 = first_tile; tile0 < a.n_tiles; tile0 += 2 * tile_step, ++pno) {
+      const int tile = tile0 + p * tile_step;
+      if (tile >= a.n_tiles) break;
       const int b = tile / tiles_per_img;
       const int t2 = tile - b * tiles_per_img;
       const int y = (t2 / a.tiles_x) * kTile2H + ly;
       const int x = (t2 % a.tiles_x) * kTile2W + lx;
       const bool valid = (x < a.W) && (y < a.H);
-      mbar_wait(&s_tfull[tr.idx], tr.phase, a.err, 3);
+      mbar_wait(&s_tfull[p], tphase, a.err, 3);
       tc_fence_after();
-      if (threadIdx.x == 0) TL(tno, 5);
-      const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(tr.idx * a.acc_cols);
+      if (threadIdx.x == 0) TL(pno, 5);
+      const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(p * a.acc_cols);
       if (!(a.timeline & 2)) conv_epilogue<EPI>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par);
       tc_fence_before();
-      mbar_arrive(&s_tempty[tr.idx]);
-      if (threadIdx.x == 0) TL(tno, 6);
-      tr.advance(a.acc_bufs);
+      mbar_arrive(&s_tempty[p]);
+      if (threadIdx.x == 0) TL(pno, 6);
+      tphase ^= 1u;
     }
   }
 
   // ---- teardown ----------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kMmaWarp0) {
     tc_fence_after();
     tmem_dealloc(tmem, static_cast<uint32_t>(a.tmem_cols));
   }

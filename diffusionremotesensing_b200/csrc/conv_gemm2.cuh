@@ -21,7 +21,7 @@ namespace drs {
 
 constexpr int kTile2W = 8;    // pixels per accumulator row group (fixed by the UMMA 8-row core-matrix group)
 constexpr int kTile2H = 16;   // row groups per M = 128 tile
-constexpr int kGemm2Threads = 192;
+constexpr int kGemm2Threads = 352;  // 8 epilogue warps + 2 MMA issuers + 1 producer
 constexpr int kMaxSubTiles = 16;
 constexpr int kMaxASlots = 8;
 constexpr int kMaxBStages = 8;

@@ -214,9 +214,10 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   a.a_slot_bytes = v.a_slot_bytes;
   a.b_stage_bytes = v.b_stage_bytes;
   a.acc_cols = v.acc_cols;
-  a.acc_bufs = (2 * v.acc_cols <= 512) ? 2 : 1;
+  if (2 * v.acc_cols > 512) return DRS_OK;  // the kernel keeps one accumulator per tile of a pair in TMEM
+  a.acc_bufs = 2;
   int alloc = 32;
-  while (alloc < a.acc_bufs * v.acc_cols) alloc <<= 1;
+  while (alloc < 2 * v.acc_cols) alloc <<= 1;
   a.tmem_cols = alloc;
   a.n_sub = g.n_sub;
   a.nsplit = g.nsplit;
@@ -224,26 +225,33 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   static const int timeline = getenv("DRS_V2_TIMELINE") ? atoi(getenv("DRS_V2_TIMELINE")) : 0;
   a.timeline = timeline;  // bit 0: record stamps, bit 1: skip the epilogue body (timing experiments only)
   a.epi = L->args.epi;
-  // shared memory: weights (resident image or a ring) + as many A slots as useful
+  // shared memory: weights (resident image or a ring) + A slots. A pair of tiles consumes slots in the order
+  // (sub-tile, tile-of-pair) and every slot is released after its own taps, so two slots per sub-tile in flight plus
+  // two of prefetch keep both issuers fed.
   const int spt = a.n_sub_tiles;
   a.b_stages = a.resident ? 1 : std::min(4, v.nkb);
   const int b_bytes = a.resident ? static_cast<int>(v.w_split_bytes) : a.b_stages * v.b_stage_bytes;
-  const int want_slots = std::min(kMaxASlots, std::max(2, 2 * spt));
-  // A single elected thread issues every MMA of a CTA (~100+ cycles per instruction at small N), so several
-  // co-resident CTAs per SM are what keeps the tensor pipe and the epilogue warps busy: take as many as TMEM and
-  // shared memory allow (at most 3), each with at least one tile's sub-tiles plus one slot of prefetch.
-  static const int max_ctas = getenv("DRS_V2_MAX_CTAS") ? atoi(getenv("DRS_V2_MAX_CTAS")) : 3;
+  const int want_slots = std::min(kMaxASlots, std::max(4, 2 * spt + 2));
+  // Each CTA already runs two MMA issuers and two epilogue groups; a second co-resident CTA is taken when TMEM and
+  // shared memory allow it.
+  static const int max_ctas = getenv("DRS_V2_MAX_CTAS") ? atoi(getenv("DRS_V2_MAX_CTAS")) : 2;
   int ctas = std::min(512 / alloc, max_ctas);
   int slots = 0;
   for (; ctas >= 1; --ctas) {
     const int budget = (227 * 1024) / ctas - 8 * 1024 - b_bytes;
-    slots = std::min(want_slots, budget / v.a_slot_bytes);
-    if (slots >= std::max(2, spt + 1) || ctas == 1) break;
+    // An even ring gives every slot to exactly one of the two issuers: a consumer that shared a slot with the
+    // other issuer would skip every second phase of its full barrier, and a parity wait cannot tell phase k from
+    // phase k + 2.
+    slots = std::min(want_slots, budget / v.a_slot_bytes) & ~1;
+    if (slots >= 4 || ctas == 1) break;
   }
+  static const int force_slots = getenv("DRS_V2_SLOTS") ? atoi(getenv("DRS_V2_SLOTS")) : 0;
+  if (force_slots > 0 && force_slots <= slots) slots = force_slots & ~1;  // debugging knob
   if (slots < 2) return DRS_OK;  // does not fit: stay on the first-generation kernel
   a.a_slots = slots;
   L->smem = static_cast<size_t>(slots) * v.a_slot_bytes + b_bytes + 1024;
-  int grid = std::min(a.n_tiles * g.nsplit, sm_count(m->device) * ctas);
+  const int pairs = (a.n_tiles + 1) / 2;
+  int grid = std::min(pairs * g.nsplit, sm_count(m->device) * ctas);
   grid -= grid % g.nsplit;
   if (grid < g.nsplit) grid = g.nsplit;
   L->grid2 = grid;
