@@ -51,7 +51,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   extern __shared__ uint8_t dyn_smem[];
   __shared__ __align__(8) uint64_t s_afull[kMaxASlots], s_aempty[kMaxASlots];
   __shared__ __align__(8) uint64_t s_bfull[kMaxBStages], s_bempty[kMaxBStages];
-  __shared__ __align__(8) uint64_t s_tfull[2], s_tempty[2];
+  __shared__ __align__(8) uint64_t s_tfull[4], s_tempty[4];  // [tile of pair][accumulator buffer]
   __shared__ __align__(8) uint64_t s_wready;
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_par[4][kMaxN];
@@ -85,7 +85,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       mbar_init(&s_bfull[s], 1);
       mbar_init(&s_bempty[s], 2);  // released by both issuers
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&s_tfull[s], 1);
       mbar_init(&s_tempty[s], 128);
     }
@@ -165,13 +165,14 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     RingPos ar{0, 0}, br{0, 0};
     if (p) ar.advance(a.a_slots);
     const uint32_t b_base16 = smem_u32(b_base) >> 4;
-    const uint32_t acc = tmem + static_cast<uint32_t>(p * a.acc_cols);
-    uint32_t tphase = 0;
+    RingPos tr{0, 0};  // accumulator buffer of this pipeline (a.acc_bufs per tile of the pair)
     int pno = 0;
     for (int tile0 = first_tile; tile0 < a.n_tiles; tile0 += 2 * tile_step, ++pno) {
       const bool valid = (tile0 + p * tile_step) < a.n_tiles;
+      const int tb = p * 2 + tr.idx;
+      const uint32_t acc = tmem + static_cast<uint32_t>((p * a.acc_bufs + tr.idx) * a.acc_cols);
       if (valid) {
-        mbar_wait(&s_tempty[p], tphase ^ 1u, a.err, 2);
+        mbar_wait(&s_tempty[tb], tr.phase ^ 1u, a.err, 2);
         tc_fence_after();
       }
       if (p == 0) TL(pno, 2);
@@ -228,10 +229,10 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
         ar.advance(a.a_slots);
         ar.advance(a.a_slots);
       }
-      if (valid && elect_one()) umma_commit(&s_tfull[p]);
+      if (valid && elect_one()) umma_commit(&s_tfull[tb]);
       __syncwarp();
       TL(pno, p ? 7 : 4);
-      tphase ^= 1u;
+      tr.advance(a.acc_bufs);
     }
   } else {
     // ---- epilogue group p: tile p of every pair ----------------------------------------------------------
@@ -240,25 +241,27 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     const int row = q * 32 + lane;
     const int lx = row & (kTile2W - 1);
     const int ly = row >> 3;
-    uint32_t tphase = 0;
+    RingPos tr{0, 0};
     int pno = 0;
     for (int tile0 = first_tile; tile0 < a.n_tiles; tile0 += 2 * tile_step, ++pno) {
       const int tile = tile0 + p * tile_step;
       if (tile >= a.n_tiles) break;
+      const int tb = p * 2 + tr.idx;
       const int b = tile / tiles_per_img;
       const int t2 = tile - b * tiles_per_img;
       const int y = (t2 / a.tiles_x) * kTile2H + ly;
       const int x = (t2 % a.tiles_x) * kTile2W + lx;
       const bool valid = (x < a.W) && (y < a.H);
-      mbar_wait(&s_tfull[p], tphase, a.err, 3);
+      mbar_wait(&s_tfull[tb], tr.phase, a.err, 3);
       tc_fence_after();
       if (threadIdx.x == 0) TL(pno, 5);
-      const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(p * a.acc_cols);
+      const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) +
+                             static_cast<uint32_t>((p * a.acc_bufs + tr.idx) * a.acc_cols);
       if (!(a.timeline & 2)) conv_epilogue<EPI>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par);
       tc_fence_before();
-      mbar_arrive(&s_tempty[p]);
+      mbar_arrive(&s_tempty[tb]);
       if (threadIdx.x == 0) TL(pno, 6);
-      tphase ^= 1u;
+      tr.advance(a.acc_bufs);
     }
   }
 

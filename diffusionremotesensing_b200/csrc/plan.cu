@@ -215,9 +215,10 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   a.b_stage_bytes = v.b_stage_bytes;
   a.acc_cols = v.acc_cols;
   if (2 * v.acc_cols > 512) return DRS_OK;  // the kernel keeps one accumulator per tile of a pair in TMEM
-  a.acc_bufs = 2;
+  // two accumulator buffers per tile of the pair when TMEM allows: the epilogue of pair i overlaps the MMAs of i + 1
+  a.acc_bufs = (4 * v.acc_cols <= 512) ? 2 : 1;
   int alloc = 32;
-  while (alloc < 2 * v.acc_cols) alloc <<= 1;
+  while (alloc < 2 * a.acc_bufs * v.acc_cols) alloc <<= 1;
   a.tmem_cols = alloc;
   a.n_sub = g.n_sub;
   a.nsplit = g.nsplit;
