@@ -68,7 +68,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -311,7 +311,7 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "image_size": S, "noise_steps": NOISE_STEPS,
                            "l2": "activations of one step (560 MB bf16) exceed the 126 MB L2; no explicit flush",
                            "parallelism": f"batch-sharded x{world}, no per-step collective"},
-                "steps_per_sec": world * K / (ms * 1e-3) / world, "sr_images_per_sec": value / (NOISE_STEPS - 1),
+                "steps_per_sec": K / (ms * 1e-3), "sr_images_per_sec": value / (NOISE_STEPS - 1),
                 "clocks": clock_info, "e2e": e2e, "gpu_launches": K * launches_per_step,
                 "launches_per_step": launches_per_step, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
@@ -323,8 +323,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", default=None, help="write the per-launch table (JSON) to this path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -124,12 +124,16 @@ int launch_bicubic_up(const float* in, float* out, int B, int C, int H, int W, i
 // ------------------------------------------------------------------------------------------------
 // conv0 + condition add -> bf16 NHWC (UNet_model_superres.py:342,355)
 // ------------------------------------------------------------------------------------------------
-__global__ void conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                             const float* __restrict__ cond, __nv_bfloat16* __restrict__ out, int nb, int nx,
-                             int ncond, int Cx, int S) {
-  __shared__ float sw[16 * 4 * 9];
-  __shared__ float sb[16];
-  for (int i = threadIdx.x; i < 16 * Cx * 9; i += blockDim.x) sw[i] = w[i];
+__global__ void __launch_bounds__(128)
+conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+             const float* __restrict__ cond, __nv_bfloat16* __restrict__ out, int nb, int nx, int ncond, int Cx, int S) {
+  // weights transposed to [ci][ky][kx][co] so the 16 output channels of one input tap are four 128-bit loads
+  __shared__ __align__(16) float sw[4 * 9 * 16];
+  __shared__ __align__(16) float sb[16];
+  for (int i = threadIdx.x; i < 16 * Cx * 9; i += blockDim.x) {
+    const int co = i / (Cx * 9), r = i % (Cx * 9);
+    sw[r * 16 + co] = w[i];
+  }
   for (int i = threadIdx.x; i < 16; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
   const long long total = static_cast<long long>(nb) * S * S;
@@ -147,14 +151,20 @@ __global__ void conv0_kernel(const float* __restrict__ x, const float* __restric
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int yy = py + ky - 1;
-      if (yy < 0 || yy >= S) continue;
+      const bool yok = (yy >= 0) && (yy < S);
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int xx = px + kx - 1;
-        if (xx < 0 || xx >= S) continue;
-        const float v = __ldg(ip + static_cast<size_t>(yy) * S + xx);
+        const float v = (yok && xx >= 0 && xx < S) ? __ldg(ip + static_cast<size_t>(yy) * S + xx) : 0.f;
+        const float4* wp = reinterpret_cast<const float4*>(sw + ((ci * 3 + ky) * 3 + kx) * 16);
 #pragma unroll
-        for (int co = 0; co < 16; ++co) acc[co] = fmaf(v, sw[(co * Cx + ci) * 9 + ky * 3 + kx], acc[co]);
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = wp[q];
+          acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+        }
       }
     }
   }
