@@ -142,6 +142,22 @@ __device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, 
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Predicated form: the instruction is issued only when `enable` is non-zero (no branch in the issue loop).
+__device__ __forceinline__ void umma_bf16_split_if(uint32_t enable, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi,
+                                                   uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "setp.ne.b32 q, %7, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(enable)
+      : "memory");
+}
 // Adds to the lower 32 bits of a shared-memory descriptor (start-address field; callers guarantee no carry).
 __device__ __forceinline__ uint64_t desc_add_lo(uint64_t d, uint32_t x) {
   uint64_t r;
