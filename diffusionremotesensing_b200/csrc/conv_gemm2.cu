@@ -41,6 +41,22 @@ struct RingPos {
   }
 };
 
+// All K-blocks of one A sub-tile with resident weights: counted loop, NK slices per K-block, no branch but the
+// back edge (every data-dependent uniform branch costs the single issuing lane ~20 cycles).
+template <int NK>
+__device__ __forceinline__ void issue_resident(const Conv2Prog& prog, int kb, int cnt, uint32_t acc, uint32_t slot16,
+                                               uint32_t b_base16) {
+  for (int i = 0; i < cnt; ++i) {
+    const KB3 K = prog.kb[kb + i];
+    const uint32_t a_lo = K.a_lo + slot16;
+    const uint32_t b_lo = K.b_lo + b_base16;
+    const uint32_t d = acc + K.col;
+    umma_bf16_split(d, a_lo, K.a_hi, b_lo, K.b_hi, K.idesc, (K.flags & KB2_INIT) ? 0u : 1u);
+#pragma unroll
+    for (int k = 1; k < NK; ++k) umma_bf16_split(d, a_lo + 2u * k, K.a_hi, b_lo + 2u * k, K.b_hi, K.idesc, 1u);
+  }
+}
+
 constexpr int kMmaWarp0 = 8;      // issuer of tile 0 of a pair (tile 1: kMmaWarp0 + 1)
 constexpr int kProducerWarp = 10;
 
@@ -148,8 +164,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
         if (!a.resident) {
           mbar_wait(&s_bempty[br.idx], br.phase ^ 1u, a.err, 1);
           if (elect_one()) {
-            mbar_expect_tx(&s_bfull[br.idx], K.b_bytes);
-            bulk_load(b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes, w_image + K.b_off, K.b_bytes,
+            mbar_expect_tx(&s_bfull[br.idx], K.b_bytes & 0xFFFFFFu);
+            bulk_load(b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes, w_image + K.b_off, K.b_bytes & 0xFFFFFFu,
                       &s_bfull[br.idx]);
           }
           __syncwarp();
@@ -186,43 +202,51 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
         }
         if (p == 0 && kb == 0) TL(pno, 3);
         const uint32_t slot16 = smem_u32(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes) >> 4;
-        int kb_end = kb;
+        const KB3 K0 = prog.kb[kb];
+        const int cnt = static_cast<int>(K0.b_bytes >> 24);  // K-blocks that read this sub-tile
         const bool leader = elect_one();
         if (leader) {
-          for (;;) {
-            const KB3 K = prog.kb[kb_end];
-            uint32_t b_lo;
-            if (a.resident) {
-              b_lo = K.b_lo + b_base16;
-            } else {
-              mbar_wait(&s_bfull[br.idx], br.phase, a.err, 2);
-              tc_fence_after();
-              b_lo = 0x10000u + b_base16 + static_cast<uint32_t>((br.idx * a.b_stage_bytes) >> 4);
-            }
-            if (valid) {
-              const uint32_t a_lo = K.a_lo + slot16;
-              const uint32_t d = acc + K.col;
-              umma_bf16_split(d, a_lo, K.a_hi, b_lo, K.b_hi, K.idesc, (K.flags & KB2_INIT) ? 0u : 1u);
-              if (K.nk >= 2) umma_bf16_split(d, a_lo + 2u, K.a_hi, b_lo + 2u, K.b_hi, K.idesc, 1u);
-              if (K.nk == 4) {
-                umma_bf16_split(d, a_lo + 4u, K.a_hi, b_lo + 4u, K.b_hi, K.idesc, 1u);
-                umma_bf16_split(d, a_lo + 6u, K.a_hi, b_lo + 6u, K.b_hi, K.idesc, 1u);
+          if (valid && a.resident) {
+            // hot path: counted loop, K = 16 slice count fixed per sub-tile, no data-dependent branch
+            const uint32_t bofs = b_base16;
+            if (K0.nk == 4)
+              issue_resident<4>(prog, kb, cnt, acc, slot16, bofs);
+            else if (K0.nk == 2)
+              issue_resident<2>(prog, kb, cnt, acc, slot16, bofs);
+            else
+              issue_resident<1>(prog, kb, cnt, acc, slot16, bofs);
+          } else {
+            for (int i = 0; i < cnt; ++i) {
+              const KB3 K = prog.kb[kb + i];
+              uint32_t b_lo = K.b_lo + b_base16;
+              if (!a.resident) {
+                mbar_wait(&s_bfull[br.idx], br.phase, a.err, 2);
+                tc_fence_after();
+                b_lo = 0x10000u + b_base16 + static_cast<uint32_t>((br.idx * a.b_stage_bytes) >> 4);
+              }
+              if (valid) {
+                const uint32_t a_lo = K.a_lo + slot16;
+                const uint32_t d = acc + K.col;
+                umma_bf16_split(d, a_lo, K.a_hi, b_lo, K.b_hi, K.idesc, (K.flags & KB2_INIT) ? 0u : 1u);
+                if (K.nk >= 2) umma_bf16_split(d, a_lo + 2u, K.a_hi, b_lo + 2u, K.b_hi, K.idesc, 1u);
+                if (K.nk == 4) {
+                  umma_bf16_split(d, a_lo + 4u, K.a_hi, b_lo + 4u, K.b_hi, K.idesc, 1u);
+                  umma_bf16_split(d, a_lo + 6u, K.a_hi, b_lo + 6u, K.b_hi, K.idesc, 1u);
+                }
+              }
+              if (!a.resident) {
+                if (valid)
+                  umma_commit(&s_bempty[br.idx]);
+                else
+                  mbar_arrive(&s_bempty[br.idx]);  // no tile 1 in the last pair: release the stage unused
+                br.advance(a.b_stages);
               }
             }
-            if (!a.resident) {
-              if (valid)
-                umma_commit(&s_bempty[br.idx]);
-              else
-                mbar_arrive(&s_bempty[br.idx]);  // no tile 1 in the last pair: release the stage unused
-              br.advance(a.b_stages);
-            }
-            ++kb_end;
-            if (K.flags & KB2_LAST) break;
           }
           if (valid) umma_commit(&s_aempty[ar.idx]);
         }
-        // every lane learns how far the elected lane went; ring positions are warp-uniform state
-        kb_end = __reduce_max_sync(0xffffffffu, kb_end);
+        const int kb_end = kb + cnt;
+        __syncwarp();
         if (!a.resident && !leader)
           for (int i = kb; i < kb_end; ++i) br.advance(a.b_stages);
         kb = kb_end;
@@ -352,7 +376,38 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int n, int iters, int unr
     if (elect_one()) {
       uint32_t tap = 0;
       for (int i = 0; i < iters; ++i) {
-        if (vary && (row0 & 0x80)) {
+        if (vary && (row0 & 0x80) && (row0 & 0x70)) {
+          // lab: the convolution kernel's issue loop, one feature at a time
+          //   0x10: nk-dependent branches   0x20: accumulate flag from the record   0x40: LAST-flag loop exit
+          const int feat = row0 & 0x70;
+          uint32_t kbi = 0;
+          for (;;) {
+            const KB3 K = tab.kb[kbi];
+            const uint32_t ao = a16 + (K.a_lo & 0xFFFFu), bo = b16b + (K.b_lo & 0xFFFFu);
+            const uint32_t d = tmem + K.col;
+            const uint32_t accf = (feat & 0x20) ? ((K.flags & KB2_INIT) ? 0u : 1u) : 1u;
+            umma_bf16_split(d, (ao & 0x3FFFu) | 0x10000u, K.a_hi, (bo & 0x3FFFu) | 0x10000u, K.b_hi, K.idesc, accf);
+            if (feat & 0x10) {
+              if (K.nk >= 2)
+                umma_bf16_split(d, ((ao + 2u) & 0x3FFFu) | 0x10000u, K.a_hi, ((bo + 2u) & 0x3FFFu) | 0x10000u, K.b_hi, K.idesc, 1u);
+              if (K.nk == 4) {
+                umma_bf16_split(d, ((ao + 4u) & 0x3FFFu) | 0x10000u, K.a_hi, ((bo + 4u) & 0x3FFFu) | 0x10000u, K.b_hi, K.idesc, 1u);
+                umma_bf16_split(d, ((ao + 6u) & 0x3FFFu) | 0x10000u, K.a_hi, ((bo + 6u) & 0x3FFFu) | 0x10000u, K.b_hi, K.idesc, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 1; k < 4; ++k)
+                umma_bf16_split(d, ((ao + 2u * k) & 0x3FFFu) | 0x10000u, K.a_hi, ((bo + 2u * k) & 0x3FFFu) | 0x10000u,
+                                K.b_hi, K.idesc, 1u);
+            }
+            ++kbi;
+            if (feat & 0x40) {
+              if (K.flags & KB2_LAST) break;
+            } else if (kbi == 9u) {
+              break;
+            }
+          }
+        } else if (vary && (row0 & 0x80)) {
           // descriptors fetched from the kernel-parameter table with a dynamic index, like the convolution kernel
           const KB3 K = tab.kb[tap];
           const uint32_t ao = a16 + (K.a_lo & 0xFFFFu), bo = b16b + (K.b_lo & 0xFFFFu);
@@ -418,6 +473,8 @@ int mma_rate(int n, int iters, int unroll4, int ctas_per_sm, long long* out_host
     tab.kb[t].a_hi = 80u | (1u << 14) | (2u << 29);
     tab.kb[t].b_hi = 64u | (1u << 14) | (2u << 29);
     tab.kb[t].idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((static_cast<uint32_t>(n) >> 3) << 17) | (8u << 24);
+    tab.kb[t].nk = 4;
+    tab.kb[t].flags = static_cast<uint8_t>((t == 0 ? (KB2_INIT | KB2_FIRST) : 0) | (t == 8 ? KB2_LAST : 0));
   }
   mma_rate_kernel<<<sms * ctas_per_sm, 128, 182 * 1024>>>(n, iters, unroll4, d, tab);
   e = cudaDeviceSynchronize();

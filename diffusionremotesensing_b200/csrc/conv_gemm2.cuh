@@ -36,7 +36,7 @@ struct __align__(16) KB3 {  // one K-block = one filter tap of one channel block
   uint8_t nk;         // K = 16 slices (ck / 16)
   uint8_t flags;      // KB2_*
   uint32_t b_off;     // byte offset of the weight tile inside one split's image (tiles are 1 KiB aligned)
-  uint32_t b_bytes;   // weight tile bytes (n * ck * 2)
+  uint32_t b_bytes;   // bits 0..23: weight tile bytes (n * ck * 2); bits 24..31 (FIRST record): K-blocks of the sub-tile
 };
 static_assert(sizeof(KB3) == 32, "KB3 must be 32 bytes");
 

@@ -378,6 +378,14 @@ struct Builder {
       }
     }
     if (max_col > 512) return;
+    // number of K-blocks of each sub-tile in the top byte of b_bytes of its FIRST record: the issuing lane's loop
+    // is counted, with no data-dependent exit
+    for (int i = 0; i < v.nkb; ++i) {
+      if (!(P.kb[i].flags & KB2_FIRST)) continue;
+      int cnt = 1;
+      while (!(P.kb[i + cnt - 1].flags & KB2_LAST)) ++cnt;
+      P.kb[i].b_bytes |= static_cast<uint32_t>(cnt) << 24;
+    }
     v.acc_cols = max_col;
     v.usable = true;
   }
