@@ -185,6 +185,8 @@ struct DrsPlan {
   bool prepared = false, begun = false;
   cudaGraphExec_t graph_noise = nullptr, graph_last = nullptr;
   cudaStream_t capture_stream = nullptr;
+  cudaStream_t side_stream = nullptr;             // attention-gate branch of the decoder stages
+  cudaEvent_t ev_fork[3] = {nullptr, nullptr, nullptr}, ev_join[3] = {nullptr, nullptr, nullptr};
   const float* last_x = nullptr;
   float* last_eps = nullptr;
 };

@@ -399,6 +399,13 @@ void plan_destroy(DrsPlan* p) {
   if (p->graph_noise) cudaGraphExecDestroy(p->graph_noise);
   if (p->graph_last) cudaGraphExecDestroy(p->graph_last);
   if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
+  if (p->side_stream) {
+    cudaStreamDestroy(p->side_stream);
+    for (int i = 0; i < 3; ++i) {
+      cudaEventDestroy(p->ev_fork[i]);
+      cudaEventDestroy(p->ev_join[i]);
+    }
+  }
   delete p;
 }
 
@@ -545,9 +552,38 @@ static int enqueue_forward(DrsPlan* p, const float* x, float* eps, cudaStream_t 
                                                  m->has_cond ? p->cond_feat.as<float>() : nullptr,
                                                  p->workspace.as<uint8_t>() + h0.offset, p->nb, p->nx,
                                                  m->has_cond ? p->ncond : 1, m->desc.x_channels, p->S, st)));
+  // Decoder stage i: [gating -> psi -> attention result] only meets [UpConvBlock conv -> transposed conv] at
+  // up_convs.i, so the gate branch runs on a side stream (forked / joined with events; inside a CUDA-graph capture
+  // this becomes two parallel branches of the graph). The gate kernels are small and latency-bound.
+  static const bool no_fork = (getenv("DRS_NO_FORK") != nullptr);
+  if (!no_fork && !p->side_stream) {
+    DRS_CUDA(cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) {
+      DRS_CUDA(cudaEventCreateWithFlags(&p->ev_fork[i], cudaEventDisableTiming));
+      DRS_CUDA(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
+    }
+  }
+  int stage = -1;
+  bool forked = false;
   for (Launch& L : p->launches) {
     const GemmSpec& g = m->gemms[L.spec];
-    const int r = launch_one(p, L, eps, st);
+    cudaStream_t use = st;
+    if (!no_fork) {
+      const bool gate = g.name.rfind("gating_signals.", 0) == 0 || g.name.rfind("attention_blocks.", 0) == 0;
+      if (g.name.rfind("gating_signals.", 0) == 0) {
+        ++stage;
+        DRS_CUDA(cudaEventRecord(p->ev_fork[stage], st));
+        DRS_CUDA(cudaStreamWaitEvent(p->side_stream, p->ev_fork[stage], 0));
+        forked = true;
+      }
+      if (gate && forked) use = p->side_stream;
+      if (forked && g.name.rfind("up_convs.", 0) == 0) {
+        DRS_CUDA(cudaEventRecord(p->ev_join[stage], p->side_stream));
+        DRS_CUDA(cudaStreamWaitEvent(st, p->ev_join[stage], 0));
+        forked = false;
+      }
+    }
+    const int r = launch_one(p, L, eps, use);
     if (r != 0) {
       set_error("launch of %s failed: %s", g.name.c_str(), cudaGetErrorString(static_cast<cudaError_t>(r)));
       return DRS_E_CUDA;
