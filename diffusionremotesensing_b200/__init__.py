@@ -8,10 +8,15 @@ from .unet import (Residual_Attention_UNet_superres, Residual_Attention_UNet_SAR
 from .diffusion import Diffusion, Diffusion_SAR_TO_NDVI, Diffusion_generation
 from .aggregation import split_aggregation_sampling, partition_blocks, gather_blocks, blend_patches
 
+from .entrypoints import (super_resolver, SAR_to_NDVI_generator, generate_per_class, prepare_scene,
+                          aggregation_super_resolver, parse_model_name, normalise_sar)
+
 Diffusion_superres = Diffusion
 
 __all__ = [
     "Residual_Attention_UNet_superres", "Residual_Attention_UNet_SAR_TO_NDVI", "Residual_Attention_UNet_generation",
     "Diffusion", "Diffusion_superres", "Diffusion_SAR_TO_NDVI", "Diffusion_generation",
     "split_aggregation_sampling", "partition_blocks", "gather_blocks", "blend_patches",
+    "super_resolver", "SAR_to_NDVI_generator", "generate_per_class", "prepare_scene", "aggregation_super_resolver",
+    "parse_model_name", "normalise_sar",
 ]

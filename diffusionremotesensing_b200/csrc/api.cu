@@ -145,6 +145,21 @@ int drs_ddpm_update(float* x_dev, const float* eps_dev, const float* noise_dev_o
   return DRS_OK;
 }
 
+int drs_noise_images(const float* x_dev, const float* eps_dev, const float* sqrt_ah_dev, const float* sqrt_1m_ah_dev,
+                     float* out_dev, int n, size_t per_sample, void* stream) {
+  if (!x_dev || !eps_dev || !sqrt_ah_dev || !sqrt_1m_ah_dev || !out_dev || n < 1) {
+    set_error("drs_noise_images: bad arguments");
+    return DRS_E_INVALID;
+  }
+  if (per_sample % 4) {
+    set_error("drs_noise_images: per-sample element count must be a multiple of 4");
+    return DRS_E_INVALID;
+  }
+  DRS_CUDA(static_cast<cudaError_t>(launch_noise_images(x_dev, eps_dev, sqrt_ah_dev, sqrt_1m_ah_dev, out_dev, n,
+                                                         per_sample, as_stream(stream))));
+  return DRS_OK;
+}
+
 int drs_blend(const float* patches_dev, const int32_t* coords4_host, int n_patches, const float* weight_dev,
               float* out_dev, float* wsum_dev, int C, int H, int W, int P, int do_clamp, void* stream) {
   if (!patches_dev || !coords4_host || !weight_dev || !out_dev || !wsum_dev || n_patches < 1 || C < 1 || C > 4) {

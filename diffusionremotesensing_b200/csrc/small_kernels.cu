@@ -335,6 +335,35 @@ int launch_ddpm_update(float* x, const float* eps, const float* noise, const flo
   return static_cast<int>(cudaGetLastError());
 }
 
+// Forward noising (train_diffusion_superres.py:183-190): x_t = sqrt(ah[t_b]) * x + sqrt(1 - ah[t_b]) * eps with the
+// per-sample factors given as arrays; multiply and add rounded separately like the reference expression.
+__global__ void noise_images_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                    const float* __restrict__ sa, const float* __restrict__ sb, float* __restrict__ out,
+                                    size_t per_sample4, size_t n4) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const size_t b = i / per_sample4;
+    const float a = __ldg(sa + b), c = __ldg(sb + b);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 ev = __ldg(reinterpret_cast<const float4*>(eps) + i);
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn(a, xv.x), __fmul_rn(c, ev.x));
+    o.y = __fadd_rn(__fmul_rn(a, xv.y), __fmul_rn(c, ev.y));
+    o.z = __fadd_rn(__fmul_rn(a, xv.z), __fmul_rn(c, ev.z));
+    o.w = __fadd_rn(__fmul_rn(a, xv.w), __fmul_rn(c, ev.w));
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+int launch_noise_images(const float* x, const float* eps, const float* sa, const float* sb, float* out, int n,
+                        size_t per_sample, cudaStream_t s) {
+  if (per_sample % 4) return static_cast<int>(cudaErrorInvalidValue);
+  const size_t n4 = static_cast<size_t>(n) * per_sample / 4;
+  int blocks = cdiv(static_cast<long long>(n4), 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  noise_images_kernel<<<blocks, 256, 0, s>>>(x, eps, sa, sb, out, per_sample / 4, n4);
+  return static_cast<int>(cudaGetLastError());
+}
+
 __global__ void advance_kernel(int* trow, int n, int dec, int* step) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) trow[i] -= dec;
   if (threadIdx.x == 0) *step -= 1;

@@ -32,6 +32,10 @@ int launch_sgemm_nt(const float* A, int lda, const float* B, int ldb, const floa
 int launch_ddpm_update(float* x, const float* eps, const float* noise, const float* coef, const int* step,
                        size_t numel, int cfg, float cfg_scale, cudaStream_t s);
 
+// out = sa[b] * x + sb[b] * eps per sample b (forward noising), fp32, separately rounded multiply / add.
+int launch_noise_images(const float* x, const float* eps, const float* sa, const float* sb, float* out, int n,
+                        size_t per_sample, cudaStream_t s);
+
 // trow[b] -= dec for b < n; *step -= 1   (one thread block; end-of-step bookkeeping kept on the device)
 int launch_advance(int* trow, int n, int dec, int* step, cudaStream_t s);
 int launch_set_rows(int* trow, const int* base_host_like_dev, int n, int* step, int step_value, int mul,

@@ -86,6 +86,29 @@ class _DiffusionBase:
         torch.save({"MODEL_STATE": target.state_dict(), "EPOCHS_RUN": epoch}, self.snapshot_path)
         print(f"Epoch {epoch} | Training snapshot saved at {self.snapshot_path}")
 
+    # -- forward process ---------------------------------------------------------
+    def noise_images(self, x, t):
+        """x_t = sqrt(alpha_hat[t]) * x + sqrt(1 - alpha_hat[t]) * eps, eps ~ N(0, 1) drawn like the reference
+        (train_diffusion_superres.py:171-190). Returns (x_t, eps). Runs the CUDA kernel when x is on a CUDA device."""
+        sqrt_ah = torch.sqrt(self.alpha_hat[t])
+        sqrt_1m = torch.sqrt(1 - self.alpha_hat[t])
+        epsilon = torch.randn_like(x, dtype=torch.float32)
+        if x.device.type != "cuda":
+            raise RuntimeError("drs_b200 noise_images runs on a CUDA device only; there is no CPU fallback")
+        x32 = x.to(torch.float32).contiguous()
+        out = torch.empty_like(x32)
+        per_sample = x32[0].numel()
+        with torch.cuda.device(x.device):
+            N.check(N.lib().drs_noise_images(N.ptr(x32), N.ptr(epsilon.contiguous()),
+                                             N.ptr(sqrt_ah.to(x.device, torch.float32).contiguous()),
+                                             N.ptr(sqrt_1m.to(x.device, torch.float32).contiguous()), N.ptr(out),
+                                             x32.shape[0], per_sample, N.stream_ptr(x.device)))
+        return out, epsilon
+
+    def sample_timesteps(self, n):
+        """Uniform integer timesteps in [1, noise_steps) (train_diffusion_superres.py:192-205)."""
+        return torch.randint(low=1, high=self.noise_steps, size=(n,))
+
     # -- per-step coefficients ---------------------------------------------------------------------------------
     def _coefficients(self):
         """c1 = 1/sqrt(alpha), c2 = (1-alpha)/sqrt(1-alpha_hat), c3 = sqrt(beta) as the reference evaluates them

@@ -120,6 +120,12 @@ int drs_plan_profile(DrsPlan* p, const float* x_dev, float* eps_dev, int iters, 
 int drs_ddpm_update(float* x_dev, const float* eps_dev, const float* noise_dev_or_null, float c1, float c2, float c3,
                     size_t numel, void* stream);
 
+/* Forward noising, train_diffusion_superres.py:183-190: out[b] = sqrt_ah[b] * x[b] + sqrt_1m_ah[b] * eps[b] for n samples
+ * of per_sample fp32 elements (multiple of 4); the per-sample factors are sqrt(alpha_hat[t_b]) and
+ * sqrt(1 - alpha_hat[t_b]) gathered by the caller. Multiply and add are rounded separately like the reference. */
+int drs_noise_images(const float* x_dev, const float* eps_dev, const float* sqrt_ah_dev, const float* sqrt_1m_ah_dev,
+                     float* out_dev, int n, size_t per_sample, void* stream);
+
 /* Aggregation_Sampling.py:91-110: Gaussian-weighted overlap blend of SR patches, summed in patch order.
  * patches_dev fp32 [n_patches, C, P, P]; coords4_host int32 [n_patches][4] = (y0, y1, x0, x1) in the output;
  * weight_dev fp32 [P, P]; out_dev fp32 [C, H, W]; wsum_dev fp32 [H, W] (scratch, also returned).
