@@ -26,6 +26,7 @@ int launch_count(const DrsPlan*);
 int launch_info(const DrsPlan*, int, char*, int, double*, double*, int*, int*);
 int plan_profile(DrsPlan*, const float*, float*, int, float*, cudaStream_t);
 int mma_rate(int, int, int, int, long long*);
+int mma_rate2(int, int, int, int, int, int, int, long long*);
 int debug_bind_and_run(DrsPlan*, const void*, int, int, int, int, void*, int, int, cudaStream_t);
 }  // namespace drs
 
@@ -273,6 +274,12 @@ int drs_debug_conv2d(const float* x_dev, const float* w_host, const float* bias_
 int drs_debug_mma_rate(int n, int iters, int unroll4, int ctas_per_sm, long long* out_host) {
   const int r = mma_rate(n, iters, unroll4, ctas_per_sm, out_host);
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "mma_rate_kernel");
+  return DRS_OK;
+}
+
+int drs_debug_mma_rate2(int n, int nk, int layout, int sbo16, int issuers, int iters, int mode, long long* out_host) {
+  const int r = mma_rate2(n, nk, layout, sbo16, issuers, iters, mode, out_host);
+  if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "mma_rate2_kernel");
   return DRS_OK;
 }
 

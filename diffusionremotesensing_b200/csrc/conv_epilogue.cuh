@@ -8,6 +8,17 @@
 
 namespace drs {
 
+#ifdef DRS_EPI_TRACE
+static __device__ long long g_epi_trace[64];
+static __device__ int g_epi_trace_on;
+#define EPI_TL(slot)                                                                    \
+  do {                                                                                  \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && g_epi_trace_on && (slot) < 64) g_epi_trace[(slot)] = clock64();                 \
+  } while (0)
+#else
+#define EPI_TL(slot) do {} while (0)
+#endif
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -36,14 +47,41 @@ __device__ __forceinline__ void ld16_global(const float* src, float* dst) {
   }
 }
 
+// Staged output path of the persistent kernel: every epilogue warp owns a 4 KiB shared-memory staging area split
+// into nbuf sub-box buffers of 32 pixel rows x sbc channels (bf16). A thread writes its pixel's channels there
+// (swizzled like the output tensor map, so the quarter-warp stores are bank-conflict free) and one lane hands each
+// finished sub-box to the TMA unit, which writes full 32-byte sectors to global memory. The per-thread 16-byte
+// global stores this replaces cost one L1 tag cycle per touched line and instruction (32 per warp store).
+struct TmaStoreCtx {
+  const CUtensorMap* map;  // output view (c, x, py, y, b): box = (sbc, 8, 1, 4, 1)
+  uint8_t* stage;          // this warp's staging area, 1024-byte aligned
+  int sbc;                 // channels per sub-box: min(64, N)
+  int nbuf;                // buffers in the staging area: 4096 / (32 * sbc * 2), at most 4
+  int buf;                 // next buffer (persists across tiles)
+  int x0, y0, b;           // box origin of this warp: tile x, tile y + 4 * quadrant, image
+};
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // taddr: TMEM address of this thread's lane quadrant at column 0 of the tile's accumulator.
 // (x, y, b): output-grid pixel of this thread; valid: inside the grid; W, H: grid size; N: channels of this
 // grid.y slice; oc_off: first output channel of the slice; s_par: [4][kMaxN] = scale, bias, scale2 | wvec, bias2.
 template <int EPI>
 __device__ __forceinline__ void conv_epilogue(const EpiArgs& e, uint32_t taddr, int x, int y, int b, bool valid, int W,
-                                              int H, int N, int oc_off, const float (*s_par)[kMaxN]) {
+                                              int H, int N, int oc_off, const float (*s_par)[kMaxN],
+                                              TmaStoreCtx* ts = nullptr) {
   if (EPI == EPI_STD) {
     const int flags = e.flags;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t st_row = 0, st_mask = 0, st_base = 0, st_bufbytes = 0;
+    if (ts) {
+      st_row = lane * static_cast<uint32_t>(ts->sbc) * 2u;         // byte offset of this thread's pixel row
+      st_mask = (ts->sbc == 64) ? 7u : ((ts->sbc == 32) ? 3u : 1u);  // SWIZZLE_128B / 64B / 32B
+      st_base = smem_u32(ts->stage);
+      st_bufbytes = 64u * static_cast<uint32_t>(ts->sbc);
+    }
     const float* te_row = nullptr;
     if (flags & (F_TE | F_PRE)) te_row = e.te + static_cast<size_t>(valid ? __ldg(e.trow + b) : 0) * e.te_stride;
     const float* te_post = te_row ? te_row + e.te_off + oc_off : nullptr;
@@ -65,6 +103,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiArgs& e, uint32_t taddr, 
       const uint32_t colbase = static_cast<uint32_t>(g * N);
       for (int c0 = 0; c0 < N; c0 += 16) {
         float v[16], w[16], p[16];
+        EPI_TL(g * 16 + (c0 >> 4) * 4 + 0);
         tmem_ld16(taddr + colbase + c0, v);
         if (flags & (F_DUAL_PRE | F_DUAL_POST)) tmem_ld16(taddr + e.col2 + c0, w);
         // per-channel vectors as 128-bit loads, issued before the TMEM wait so their latency overlaps
@@ -73,6 +112,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiArgs& e, uint32_t taddr, 
         ld16_shared(&s_par[1][c0], bi);
         if (flags & F_PRE) ld16_global(te_pre + c0, p);
         tmem_ld_wait();
+        EPI_TL(g * 16 + (c0 >> 4) * 4 + 1);
         if (flags & F_ROWSCALE) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= rs;
@@ -105,11 +145,43 @@ __device__ __forceinline__ void conv_epilogue(const EpiArgs& e, uint32_t taddr, 
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-        if (valid) {
+        EPI_TL(g * 16 + (c0 >> 4) * 4 + 2);
+        if (ts) {
+          const int cs = c0 & (ts->sbc - 1);  // first channel of this chunk inside its sub-box
+          if (cs == 0) {
+            // the buffer about to be overwritten must have been read by the store issued nbuf sub-boxes ago
+            if (lane == 0) {
+              if (ts->nbuf == 1)
+                bulk_wait_read<0>();
+              else if (ts->nbuf == 2)
+                bulk_wait_read<1>();
+              else
+                bulk_wait_read<3>();
+            }
+            __syncwarp();
+          }
+          const uint32_t buf = st_base + static_cast<uint32_t>(ts->buf) * st_bufbytes;
+          const uint32_t off = st_row + static_cast<uint32_t>(cs) * 2u;
+          const uint32_t sw = ((off >> 7) & st_mask) << 4;
+          st_shared_v4(buf + (off ^ sw), pk[0], pk[1], pk[2], pk[3]);
+          st_shared_v4(buf + ((off + 16u) ^ sw), pk[4], pk[5], pk[6], pk[7]);
+          if (cs + 16 == ts->sbc) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int cc = ((e.oscale == 2) ? (g & 1) * e.OC : 0) + oc_off + c0 + 16 - ts->sbc;
+              tma_store_5d(ts->map, reinterpret_cast<const void*>(ts->stage + static_cast<size_t>(ts->buf) * st_bufbytes),
+                           cc, ts->x0, (e.oscale == 2) ? (g >> 1) : 0, ts->y0, ts->b);
+              bulk_commit();
+            }
+            ts->buf = (ts->buf + 1 == ts->nbuf) ? 0 : ts->buf + 1;
+          }
+        } else if (valid) {
           uint4* o = reinterpret_cast<uint4*>(optr + c0);
           o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
+        EPI_TL(g * 16 + (c0 >> 4) * 4 + 3);
       }
     }
   } else if (EPI == EPI_PSI) {
@@ -149,6 +221,182 @@ __device__ __forceinline__ void conv_epilogue(const EpiArgs& e, uint32_t taddr, 
       const size_t pix = static_cast<size_t>(y) * W + x;
       float* o = reinterpret_cast<float*>(e.out);
       for (int k = 0; k < e.nvec; ++k) o[(static_cast<size_t>(b) * e.nvec + k) * plane + pix] = acc[k] + __ldg(e.bvec + k);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// EPI_STD with the flag word known at compile time (persistent kernel): no per-chunk flag tests, the time-embedding
+// row comes from a per-warp shared-memory copy (s_te, filled before the accumulator wait), and the TMEM load of chunk
+// i + 1 is in flight while chunk i is scaled, packed and stored.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld16_raw(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// The wait names the destination registers as read-write operands, so the compiler can neither read nor copy them
+// before the asynchronous load has landed.
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[16], uint32_t (&q)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]),
+                 "+r"(q[8]), "+r"(q[9]), "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15])
+               :
+               : "memory");
+}
+
+template <int FL>
+struct StdEpilogue {
+  static constexpr bool kDual = (FL & (F_DUAL_PRE | F_DUAL_POST)) != 0;
+  const EpiArgs& e;
+  const float (*s_par)[kMaxN];
+  const float* s_te;      // this warp's staged time-embedding row (F_TE)
+  const float* te_pre;    // this thread's border-class row (F_PRE)
+  TmaStoreCtx* ts;
+  __nv_bfloat16* orow;    // direct stores: this thread's output pixel of the current group
+  uint32_t lane, st_row, st_mask, st_base, st_bufbytes;
+  float rs;
+  bool valid;
+  int oc_off;
+
+  // scale / pack / store one chunk of 16 channels starting at channel c0 of column group g
+  __device__ __forceinline__ void chunk(const uint32_t (&rv)[16], const uint32_t (&rw)[16], int g, int c0) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = c0 + 4 * q;
+      const float4 sc = *reinterpret_cast<const float4*>(&s_par[0][c]);
+      const float4 bi = *reinterpret_cast<const float4*>(&s_par[1][c]);
+      float x0 = __uint_as_float(rv[4 * q + 0]), x1 = __uint_as_float(rv[4 * q + 1]);
+      float x2 = __uint_as_float(rv[4 * q + 2]), x3 = __uint_as_float(rv[4 * q + 3]);
+      if (FL & F_ROWSCALE) { x0 *= rs; x1 *= rs; x2 *= rs; x3 *= rs; }
+      if (FL & F_PRE) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(te_pre + c));
+        x0 += t.x; x1 += t.y; x2 += t.z; x3 += t.w;
+      }
+      x0 = fmaf(x0, sc.x, bi.x); x1 = fmaf(x1, sc.y, bi.y); x2 = fmaf(x2, sc.z, bi.z); x3 = fmaf(x3, sc.w, bi.w);
+      if (FL & F_DUAL_PRE) {
+        const float4 s2 = *reinterpret_cast<const float4*>(&s_par[2][c]);
+        x0 = fmaf(__uint_as_float(rw[4 * q + 0]), s2.x, x0); x1 = fmaf(__uint_as_float(rw[4 * q + 1]), s2.y, x1);
+        x2 = fmaf(__uint_as_float(rw[4 * q + 2]), s2.z, x2); x3 = fmaf(__uint_as_float(rw[4 * q + 3]), s2.w, x3);
+      }
+      if (FL & F_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+      if (FL & F_DUAL_POST) {
+        const float4 b2 = *reinterpret_cast<const float4*>(&s_par[3][c]);
+        x0 += __uint_as_float(rw[4 * q + 0]) + b2.x; x1 += __uint_as_float(rw[4 * q + 1]) + b2.y;
+        x2 += __uint_as_float(rw[4 * q + 2]) + b2.z; x3 += __uint_as_float(rw[4 * q + 3]) + b2.w;
+      }
+      if (FL & F_TE) {
+        const float4 t = *reinterpret_cast<const float4*>(s_te + c);
+        x0 += t.x; x1 += t.y; x2 += t.z; x3 += t.w;
+      }
+      pk[2 * q] = pack_bf16(x0, x1);
+      pk[2 * q + 1] = pack_bf16(x2, x3);
+    }
+    if (ts) {
+      const int cs = c0 & (ts->sbc - 1);  // first channel of this chunk inside its sub-box
+      if (cs == 0) {
+        // the buffer about to be overwritten must have been read by the store issued nbuf sub-boxes ago
+        if (lane == 0) {
+          if (ts->nbuf == 1)
+            bulk_wait_read<0>();
+          else if (ts->nbuf == 2)
+            bulk_wait_read<1>();
+          else
+            bulk_wait_read<3>();
+        }
+        __syncwarp();
+      }
+      const uint32_t buf = st_base + static_cast<uint32_t>(ts->buf) * st_bufbytes;
+      const uint32_t off = st_row + static_cast<uint32_t>(cs) * 2u;
+      const uint32_t sw = ((off >> 7) & st_mask) << 4;
+      st_shared_v4(buf + (off ^ sw), pk[0], pk[1], pk[2], pk[3]);
+      st_shared_v4(buf + ((off + 16u) ^ sw), pk[4], pk[5], pk[6], pk[7]);
+      if (cs + 16 == ts->sbc) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const int cc = ((e.oscale == 2) ? (g & 1) * e.OC : 0) + oc_off + c0 + 16 - ts->sbc;
+          tma_store_5d(ts->map, reinterpret_cast<const void*>(ts->stage + static_cast<size_t>(ts->buf) * st_bufbytes), cc,
+                       ts->x0, (e.oscale == 2) ? (g >> 1) : 0, ts->y0, ts->b);
+          bulk_commit();
+        }
+        ts->buf = (ts->buf + 1 == ts->nbuf) ? 0 : ts->buf + 1;
+      }
+    } else if (valid) {
+      uint4* o = reinterpret_cast<uint4*>(orow + c0);
+      o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+  }
+};
+
+template <int FL>
+__device__ __forceinline__ void conv_epilogue_std_ct(const EpiArgs& e, uint32_t taddr, int x, int y, int b, bool valid,
+                                                     int W, int H, int N, int oc_off, const float (*s_par)[kMaxN],
+                                                     const float* s_te, TmaStoreCtx* ts) {
+  StdEpilogue<FL> E{e, s_par, s_te, nullptr, ts, nullptr, threadIdx.x & 31u, 0, 0, 0, 0, 1.0f, valid, oc_off};
+  if (ts) {
+    E.st_row = E.lane * static_cast<uint32_t>(ts->sbc) * 2u;
+    E.st_mask = (ts->sbc == 64) ? 7u : ((ts->sbc == 32) ? 3u : 1u);
+    E.st_base = smem_u32(ts->stage);
+    E.st_bufbytes = 64u * static_cast<uint32_t>(ts->sbc);
+  }
+  if (FL & F_PRE) {
+    const int ry = (y == 0) ? 0 : ((y == H - 1) ? 2 : 1);
+    const int rx = (x == 0) ? 0 : ((x == W - 1) ? 2 : 1);
+    E.te_pre = e.te + static_cast<size_t>(valid ? __ldg(e.trow + b) : 0) * e.te_stride + e.pre_off +
+               (ry * 3 + rx) * e.OC + oc_off;
+  }
+  if ((FL & F_ROWSCALE) && valid)
+    E.rs = __ldg(e.psi + (static_cast<size_t>(b) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1));
+
+  uint32_t va[16], vb[16], wa[16], wb[16];
+  const int n_groups = e.n_groups;
+  tmem_ld16_raw(taddr, va);
+  if (StdEpilogue<FL>::kDual) tmem_ld16_raw(taddr + e.col2, wa);
+  for (int g = 0; g < n_groups; ++g) {
+    const int oy = (e.oscale == 2) ? (2 * y + (g >> 1)) : y;
+    const int ox = (e.oscale == 2) ? (2 * x + (g & 1)) : x;
+    E.orow = reinterpret_cast<__nv_bfloat16*>(e.out) + ((static_cast<size_t>(b) * e.OH + oy) * e.OW + ox) * e.OC + oc_off;
+    const uint32_t colbase = taddr + static_cast<uint32_t>(g * N);
+    const bool more_groups = (g + 1 < n_groups);
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      // chunk A = [c0, c0 + 16): its load is in flight; start chunk B, work on A, then the same with roles swapped
+      const bool has_b = (c0 + 16 < N);
+      if (StdEpilogue<FL>::kDual) tmem_ld_wait32(va, wa); else tmem_ld_wait16(va);
+      if (has_b) {
+        tmem_ld16_raw(colbase + c0 + 16, vb);
+        if (StdEpilogue<FL>::kDual) tmem_ld16_raw(taddr + e.col2 + c0 + 16, wb);
+      }
+      E.chunk(va, wa, g, c0);
+      if (has_b) {
+        if (StdEpilogue<FL>::kDual) tmem_ld_wait32(vb, wb); else tmem_ld_wait16(vb);
+        if (c0 + 32 < N) {
+          tmem_ld16_raw(colbase + c0 + 32, va);
+          if (StdEpilogue<FL>::kDual) tmem_ld16_raw(taddr + e.col2 + c0 + 32, wa);
+        } else if (more_groups) {
+          tmem_ld16_raw(colbase + N, va);
+          if (StdEpilogue<FL>::kDual) tmem_ld16_raw(taddr + e.col2, wa);
+        }
+        E.chunk(vb, wb, g, c0 + 16);
+      } else if (more_groups) {
+        tmem_ld16_raw(colbase + N, va);  // N == 16: no overlap (does not occur in the three UNets)
+        if (StdEpilogue<FL>::kDual) tmem_ld16_raw(taddr + e.col2, wa);
+      }
     }
   }
 }

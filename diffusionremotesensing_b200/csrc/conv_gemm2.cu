@@ -13,6 +13,7 @@
 // warps, so spinning or ALU-heavy epilogue warps never starve the issuer they wait for.
 // Rings: A slots (full/empty, filled in the order (sub-tile, tile-of-pair)), B stages (full / empty-by-both-issuers,
 // streamed mode), TMEM buffer p (full/empty) for tile p of the pair.
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_epilogue.cuh"
@@ -60,10 +61,12 @@ __device__ __forceinline__ void issue_resident(const Conv2Prog& prog, int kb, in
 constexpr int kMmaWarp0 = 8;      // issuer of tile 0 of a pair (tile 1: kMmaWarp0 + 1)
 constexpr int kProducerWarp = 10;
 
-template <int EPI>
+// FL: EPI_STD flag word known at compile time (the seven combinations the UNets use), or -1 for the generic epilogue.
+template <int EPI, int FL>
 __global__ void __launch_bounds__(kGemm2Threads)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
-                  const __grid_constant__ Conv2Args a, const __grid_constant__ Conv2Prog prog) {
+                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ Conv2Args a,
+                  const __grid_constant__ Conv2Prog prog) {
   extern __shared__ uint8_t dyn_smem[];
   __shared__ __align__(8) uint64_t s_afull[kMaxASlots], s_aempty[kMaxASlots];
   __shared__ __align__(8) uint64_t s_bfull[kMaxBStages], s_bempty[kMaxBStages];
@@ -71,6 +74,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   __shared__ __align__(8) uint64_t s_wready;
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_par[4][kMaxN];
+  constexpr bool kStageTe = (EPI == EPI_STD && FL >= 0 && (FL & F_TE));
+  __shared__ __align__(16) float s_te[kStageTe ? 8 : 1][kStageTe ? kMaxN : 4];  // per epilogue warp
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
@@ -93,6 +98,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&map0);
     tma_prefetch_desc(&map1);
+    if (a.store_sbc) tma_prefetch_desc(&map_out);
     for (int s = 0; s < a.a_slots; ++s) {
       mbar_init(&s_afull[s], 1);
       mbar_init(&s_aempty[s], 1);
@@ -267,6 +273,14 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     const int ly = row >> 3;
     RingPos tr{0, 0};
     int pno = 0;
+    TmaStoreCtx ts;
+    ts.map = &map_out;
+    ts.sbc = a.store_sbc;
+    ts.nbuf = a.store_sbc ? min(4, kStageBytesPerWarp / (64 * a.store_sbc)) : 1;
+    ts.buf = 0;
+    // staging areas follow the weight region (both 1024-byte aligned)
+    ts.stage = b_base + (a.resident ? a.w_split_bytes : static_cast<uint32_t>(a.b_stages * a.b_stage_bytes)) +
+               static_cast<size_t>(warp) * kStageBytesPerWarp;
     for (int tile0 = first_tile; tile0 < a.n_tiles; tile0 += 2 * tile_step, ++pno) {
       const int tile = tile0 + p * tile_step;
       if (tile >= a.n_tiles) break;
@@ -276,17 +290,40 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       const int y = (t2 / a.tiles_x) * kTile2H + ly;
       const int x = (t2 % a.tiles_x) * kTile2W + lx;
       const bool valid = (x < a.W) && (y < a.H);
+      if (kStageTe) {
+        // this tile's time-embedding row -> the warp's shared copy (latency hidden behind the accumulator wait)
+        __syncwarp();
+        const float* src = e.te + static_cast<size_t>(__ldg(e.trow + b)) * e.te_stride + e.te_off + oc_off;
+        for (int c = lane * 4; c < a.n_sub; c += 128)
+          *reinterpret_cast<float4*>(&s_te[warp][c]) = __ldg(reinterpret_cast<const float4*>(src + c));
+        __syncwarp();
+      }
       mbar_wait(&s_tfull[tb], tr.phase, a.err, 3);
       tc_fence_after();
       if (threadIdx.x == 0) TL(pno, 5);
       const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>((p * a.acc_bufs + tr.idx) * a.acc_cols);
-      if (!(a.timeline & 2)) conv_epilogue<EPI>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par);
+      ts.x0 = (t2 % a.tiles_x) * kTile2W;
+      ts.y0 = (t2 / a.tiles_x) * kTile2H + q * 4;
+      ts.b = b;
+#ifdef DRS_EPI_TRACE
+      if (threadIdx.x == 0 && blockIdx.x == 0) g_epi_trace_on = ((a.timeline & 1) && pno == 3) ? 1 : 0;
+#endif
+      if (!(a.timeline & 2)) {
+        if constexpr (EPI == EPI_STD && FL >= 0)
+          conv_epilogue_std_ct<FL>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par, s_te[kStageTe ? warp : 0],
+                                   a.store_sbc ? &ts : nullptr);
+        else
+          conv_epilogue<EPI>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par,
+                             (EPI == EPI_STD && a.store_sbc) ? &ts : nullptr);
+      }
       tc_fence_before();
       mbar_arrive(&s_tempty[tb]);
       if (threadIdx.x == 0) TL(pno, 6);
       tr.advance(a.acc_bufs);
     }
+    // the staging areas must outlive the TMA unit's reads
+    if (EPI == EPI_STD && a.store_sbc && lane == 0) bulk_wait_read<0>();
   }
 
   // ---- teardown ----------------------------------------------------------------------------------
@@ -298,32 +335,60 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   }
 }
 
-static constexpr int kMaxDynSmem2 = 220 * 1024;
+static constexpr int kMaxDynSmem2 = 214 * 1024;
+
+// every instantiation: (EPI, FL)
+#define DRS_GEMM2_VARIANTS(X)                     \
+  X(EPI_STD, -1)                                  \
+  X(EPI_STD, 0)                                   \
+  X(EPI_STD, F_RELU)                              \
+  X(EPI_STD, F_RELU | F_TE)                       \
+  X(EPI_STD, F_RELU | F_TE | F_DUAL_POST)         \
+  X(EPI_STD, F_RELU | F_DUAL_PRE)                 \
+  X(EPI_STD, F_ROWSCALE)                          \
+  X(EPI_STD, F_RELU | F_PRE)                      \
+  X(EPI_PSI, -1)                                  \
+  X(EPI_OUT, -1)
 
 int conv_gemm2_set_smem_limits() {
-  cudaError_t e;
-  e = cudaFuncSetAttribute(conv_gemm2_kernel<EPI_STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem2);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  e = cudaFuncSetAttribute(conv_gemm2_kernel<EPI_PSI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem2);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  e = cudaFuncSetAttribute(conv_gemm2_kernel<EPI_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem2);
+  cudaError_t e = cudaSuccess;
+#define X(EPI, FL)                                                                                              \
+  if (e == cudaSuccess)                                                                                         \
+    e = cudaFuncSetAttribute(conv_gemm2_kernel<EPI, (FL)>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem2);
+  DRS_GEMM2_VARIANTS(X)
+#undef X
   return static_cast<int>(e);
 }
 
 int conv_gemm2_read_timeline(long long* host, int n) {
   if (n > 64 * 8) n = 64 * 8;
+#ifdef DRS_EPI_TRACE
+  // debug builds: entries 256.. carry the per-chunk epilogue stamps of thread 0 of CTA 0 in its fourth tile pair
+  cudaError_t e = cudaMemcpyFromSymbol(host, g_timeline, n * sizeof(long long));
+  if (e == cudaSuccess && n >= 320) e = cudaMemcpyFromSymbol(host + 256, g_epi_trace, 64 * sizeof(long long));
+  return static_cast<int>(e);
+#else
   return static_cast<int>(cudaMemcpyFromSymbol(host, g_timeline, n * sizeof(long long)));
+#endif
 }
 
-int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& map1, const Conv2Args& args,
-                      const Conv2Prog& prog, int grid, size_t smem_bytes, cudaStream_t stream) {
+int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& map1, const CUtensorMap& map_out,
+                      const Conv2Args& args, const Conv2Prog& prog, int grid, size_t smem_bytes, cudaStream_t stream) {
   dim3 g(static_cast<unsigned>(grid), 1, 1);
   dim3 block(kGemm2Threads, 1, 1);
-  switch (epi_kind) {
-    case EPI_STD: conv_gemm2_kernel<EPI_STD><<<g, block, smem_bytes, stream>>>(map0, map1, args, prog); break;
-    case EPI_PSI: conv_gemm2_kernel<EPI_PSI><<<g, block, smem_bytes, stream>>>(map0, map1, args, prog); break;
-    case EPI_OUT: conv_gemm2_kernel<EPI_OUT><<<g, block, smem_bytes, stream>>>(map0, map1, args, prog); break;
-    default: return static_cast<int>(cudaErrorInvalidValue);
+  static const bool generic = (getenv("DRS_V2_GENERIC_EPILOGUE") != nullptr);
+  const int fl = (epi_kind == EPI_STD && !generic) ? args.epi.flags : -1;
+  bool done = false;
+#define X(EPI, FL)                                                                                      \
+  if (!done && epi_kind == EPI && fl == (FL)) {                                                         \
+    conv_gemm2_kernel<EPI, (FL)><<<g, block, smem_bytes, stream>>>(map0, map1, map_out, args, prog);    \
+    done = true;                                                                                        \
+  }
+  DRS_GEMM2_VARIANTS(X)
+#undef X
+  if (!done) {
+    if (epi_kind != EPI_STD) return static_cast<int>(cudaErrorInvalidValue);
+    conv_gemm2_kernel<EPI_STD, -1><<<g, block, smem_bytes, stream>>>(map0, map1, map_out, args, prog);
   }
   return static_cast<int>(cudaGetLastError());
 }

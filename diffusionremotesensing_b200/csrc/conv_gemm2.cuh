@@ -83,12 +83,17 @@ struct Conv2Args {
   int acc_cols;             // columns one tile's accumulators use
   int acc_bufs;             // 1 or 2
   int n_sub, nsplit;
+  int store_sbc;            // EPI_STD: channels per TMA-store sub-box (0: per-thread global stores, no staging)
   int timeline;             // debug: CTA 0 records clock stamps (DRS_V2_TIMELINE)
   int* err;
   EpiArgs epi;
 };
 
-int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& map1, const Conv2Args& args,
+constexpr int kStageBytesPerWarp = 4096;  // staging area of one epilogue warp (TMA-store path)
+constexpr int kStageBytes = 8 * kStageBytesPerWarp;
+
+int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& map1, const CUtensorMap& map_out,
+                      const Conv2Args& args,
                       const Conv2Prog& prog, int grid, size_t smem_bytes, cudaStream_t stream);
 int conv_gemm2_set_smem_limits();
 int conv_gemm2_read_timeline(long long* host, int n);

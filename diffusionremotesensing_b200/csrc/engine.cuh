@@ -149,7 +149,7 @@ struct ActTensor {
 
 struct Launch {
   int spec = -1;  // index into model->gemms, or -1 for the conv0 kernel
-  CUtensorMap map0, map1;
+  CUtensorMap map0, map1, map_out;  // map_out: output view of the TMA-store epilogue (second-generation kernel)
   ConvArgs args;
   int n_tiles = 0;
   size_t smem = 0;

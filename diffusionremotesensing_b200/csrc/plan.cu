@@ -224,7 +224,10 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   a.nsplit = g.nsplit;
   a.err = p->d_err;
   static const int timeline = getenv("DRS_V2_TIMELINE") ? atoi(getenv("DRS_V2_TIMELINE")) : 0;
-  a.timeline = timeline;  // bit 0: record stamps, bit 1: skip the epilogue body (timing experiments only)
+  // bit 0: record stamps, bit 1: skip the epilogue body (timing experiments only); DRS_V2_TIMELINE_LAYER restricts
+  // the recording to launches whose name contains the given substring
+  static const char* const tl_layer = getenv("DRS_V2_TIMELINE_LAYER");
+  a.timeline = (!tl_layer || g.name.find(tl_layer) != std::string::npos) ? timeline : 0;
   a.epi = L->args.epi;
   // shared memory: weights (resident image or a ring) + A slots. A pair of tiles consumes slots in the order
   // (sub-tile, tile-of-pair) and every slot is released after its own taps, so two slots per sub-tile in flight plus
@@ -233,24 +236,41 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   a.b_stages = a.resident ? 1 : std::min(4, v.nkb);
   const int b_bytes = a.resident ? static_cast<int>(v.w_split_bytes) : a.b_stages * v.b_stage_bytes;
   const int want_slots = std::min(kMaxASlots, std::max(4, 2 * spt + 2));
+  // Staged TMA-store epilogue (EPI_STD, bf16 NHWC output whose tiles never straddle two images): 4 KiB per
+  // epilogue warp, taken when at least four A slots still fit.
+  static const bool no_stage = (getenv("DRS_V2_NO_TMA_STORE") != nullptr);
+  const bool can_stage = !no_stage && g.epi_kind == EPI_STD && (g.n_sub % 16) == 0 &&
+                         (g.oscale == 1 || (a.epi.OW % 2 == 0 && a.epi.OH % 2 == 0));
+  int stage_bytes = 0;
   // Each CTA already runs two MMA issuers and two epilogue groups; a second co-resident CTA is taken when TMEM and
   // shared memory allow it.
   static const int max_ctas = getenv("DRS_V2_MAX_CTAS") ? atoi(getenv("DRS_V2_MAX_CTAS")) : 2;
   int ctas = std::min(512 / alloc, max_ctas);
   int slots = 0;
   for (; ctas >= 1; --ctas) {
-    const int budget = (227 * 1024) / ctas - 8 * 1024 - b_bytes;
+    const int budget = (227 * 1024) / ctas - 14 * 1024 - b_bytes;
     // An even ring gives every slot to exactly one of the two issuers: a consumer that shared a slot with the
     // other issuer would skip every second phase of its full barrier, and a parity wait cannot tell phase k from
     // phase k + 2.
-    slots = std::min(want_slots, budget / v.a_slot_bytes) & ~1;
+    stage_bytes = 0;
+    if (can_stage && (((budget - kStageBytes) / v.a_slot_bytes) & ~1) >= 4) stage_bytes = kStageBytes;
+    slots = std::min(want_slots, (budget - stage_bytes) / v.a_slot_bytes) & ~1;
     if (slots >= 4 || ctas == 1) break;
   }
   static const int force_slots = getenv("DRS_V2_SLOTS") ? atoi(getenv("DRS_V2_SLOTS")) : 0;
   if (force_slots > 0 && force_slots <= slots) slots = force_slots & ~1;  // debugging knob
   if (slots < 2) return DRS_OK;  // does not fit: stay on the first-generation kernel
   a.a_slots = slots;
-  L->smem = static_cast<size_t>(slots) * v.a_slot_bytes + b_bytes + 1024;
+  a.store_sbc = 0;
+  if (stage_bytes) {
+    a.store_sbc = std::min(64, g.n_sub);
+    const int r = make_map(&L->map_out, a.epi.out, p->nb, a.epi.OH, a.epi.OW, a.epi.OC, g.oscale == 2, a.store_sbc,
+                           kTile2W, 4, 1, 1);
+    if (r != DRS_OK) return r;
+  } else {
+    L->map_out = L->map0;
+  }
+  L->smem = static_cast<size_t>(slots) * v.a_slot_bytes + b_bytes + stage_bytes + 1024;
   const int pairs = (a.n_tiles + 1) / 2;
   int grid = std::min(pairs * g.nsplit, sm_count(m->device) * ctas);
   grid -= grid % g.nsplit;
@@ -265,7 +285,7 @@ static int launch_one(const DrsPlan* p, const Launch& L, float* eps, cudaStream_
   if (L.use_v2) {
     Conv2Args a = L.args2;
     if (g.epi_kind == EPI_OUT && eps) a.epi.out = eps;
-    return launch_conv_gemm2(g.epi_kind, L.map0, L.map1, a, *L.prog2, L.grid2, L.smem, st);
+    return launch_conv_gemm2(g.epi_kind, L.map0, L.map1, L.map_out, a, *L.prog2, L.grid2, L.smem, st);
   }
   ConvArgs a = L.args;
   if (g.epi_kind == EPI_OUT && eps) a.epi.out = eps;

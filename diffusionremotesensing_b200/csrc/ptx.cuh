@@ -43,10 +43,26 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
-// Bounded spin: a pipeline bug must never hang the GPU. On timeout the error word is set and the
+// Same with a suspend-time hint (ns): the hardware parks the thread until the phase completes or the hint expires, so a
+// waiting warp does not compete for issue slots with the warps that share its scheduler.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a pipeline bug must never hang the GPU. On timeout the error word is set and the
 // caller keeps going (results are garbage, the host reports the error after the launch).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
   if (mbar_try_wait(bar, parity)) return;
+#ifdef DRS_MBAR_SPIN
   const long long t0 = clock64();
   int polls = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -57,6 +73,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
       return;
     }
   }
+#else
+  // each try parks the thread for up to ~20 us; 2^15 tries bound the wait to roughly half a second
+  for (int tries = 0; tries < (1 << 15); ++tries) {
+    if (mbar_try_wait_hint(bar, parity, 20000u)) return;
+    if (err && (tries & 15) == 15 && *reinterpret_cast<volatile int*>(err) != 0) return;
+  }
+  if (err) atomicCAS(err, 0, code);
+#endif
 }
 
 // One lane of a fully converged warp (warp-uniform control flow keeps descriptors in uniform registers).
@@ -96,6 +120,22 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
       ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+
+// 5-D tiled store shared -> global (bulk async group); out-of-range parts of the box are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(map)),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Waits until at most N of this thread's bulk groups still have to READ their shared-memory source.
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -151,6 +151,12 @@ int drs_debug_timeline(long long* out_host, int n);
  * last instruction was issued, out_host[1] = cycles until all completed (CTA 0). Synchronises the device. */
 int drs_debug_mma_rate(int n, int iters, int unroll4, int ctas_per_sm, long long* out_host);
 
+/* Debug micro-benchmark, second form: `issuers` (1..4) warps of one CTA per SM each issue `iters` K-blocks of `nk`
+ * MMAs (M=128 x n x K=16) with the given swizzle `layout` code (2 = 128 B, 4 = 64 B, 6 = 32 B rows) and A group stride
+ * `sbo16` (16-byte units). mode 0: descriptors in registers; 1: 32-byte table record per K-block; 2: packed 64-bit
+ * record. out_host as above. */
+int drs_debug_mma_rate2(int n, int nk, int layout, int sbo16, int issuers, int iters, int mode, long long* out_host);
+
 /* Intermediate activations of the last forward, converted to fp32 NCHW (tests only). Returns numel written or <0.
  * name: "h0","b0.h","b0.out","d0","b1.out","d1","b2.out","d2","bn.out","g0","psi0","att0","uc0","ut0","x0",... */
 int64_t drs_debug_fetch(DrsPlan* p, const char* name, float* out_dev, int64_t capacity, void* stream);
