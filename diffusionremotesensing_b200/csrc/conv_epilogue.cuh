@@ -364,10 +364,21 @@ __device__ __forceinline__ void conv_epilogue_std_ct(const EpiArgs& e, uint32_t 
   if ((FL & F_ROWSCALE) && valid)
     E.rs = __ldg(e.psi + (static_cast<size_t>(b) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1));
 
-  uint32_t va[16], vb[16], wa[16], wb[16];
   const int n_groups = e.n_groups;
+  if (StdEpilogue<FL>::kDual) {
+    // two accumulators per chunk: single-buffered (32 registers), which keeps the kernel at two CTAs per SM
+    uint32_t v[16], w[16];
+    E.orow = reinterpret_cast<__nv_bfloat16*>(e.out) + ((static_cast<size_t>(b) * e.OH + y) * e.OW + x) * e.OC + oc_off;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      tmem_ld16_raw(taddr + c0, v);
+      tmem_ld16_raw(taddr + e.col2 + c0, w);
+      tmem_ld_wait32(v, w);
+      E.chunk(v, w, 0, c0);
+    }
+    return;
+  }
+  uint32_t va[16], vb[16], wa[16], wb[16];
   tmem_ld16_raw(taddr, va);
-  if (StdEpilogue<FL>::kDual) tmem_ld16_raw(taddr + e.col2, wa);
   for (int g = 0; g < n_groups; ++g) {
     const int oy = (e.oscale == 2) ? (2 * y + (g >> 1)) : y;
     const int ox = (e.oscale == 2) ? (2 * x + (g & 1)) : x;

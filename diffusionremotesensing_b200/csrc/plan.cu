@@ -465,7 +465,7 @@ int cond_encode(DrsPlan* p, const float* cond, cudaStream_t st) {
     DRS_CUDA(static_cast<cudaError_t>(launch_bicubic_up(t0, t1, n, Cc, h, w, p->mag, st)));
     enc = t1;
   }
-  DRS_CUDA(static_cast<cudaError_t>(conv(m->cond_conv, enc, nullptr, p->cond_feat.as<float>(), p->S, p->S, 0, 1)));
+  DRS_CUDA(static_cast<cudaError_t>(conv(m->cond_conv, enc, nullptr, p->cond_feat.as<float>(), p->S, p->S, 0, 0)));
   return DRS_OK;
 }
 
@@ -568,7 +568,7 @@ int time_embed(DrsPlan* p, const float* t_dev, const int* label_dev, cudaStream_
 static int enqueue_forward(DrsPlan* p, const float* x, float* eps, cudaStream_t st) {
   const DrsModel* m = p->m;
   const ActTensor& h0 = p->acts.at("h0");
-  DRS_CUDA(static_cast<cudaError_t>(launch_conv0(x, m->f(m->conv0.w), m->f(m->conv0.b),
+  DRS_CUDA(static_cast<cudaError_t>(launch_conv0(x, m->fblob.data() + m->conv0.w, m->fblob.data() + m->conv0.b,
                                                  m->has_cond ? p->cond_feat.as<float>() : nullptr,
                                                  p->workspace.as<uint8_t>() + h0.offset, p->nb, p->nx,
                                                  m->has_cond ? p->ncond : 1, m->desc.x_channels, p->S, st)));
@@ -871,7 +871,7 @@ int plan_profile(DrsPlan* p, const float* x, float* eps, int iters, float* ms_ou
   for (int it = 0; it < iters && rc == DRS_OK; ++it) {
     const ActTensor& h0 = p->acts.at("h0");
     cudaEventRecord(ev[0], st);
-    launch_conv0(x, m->f(m->conv0.w), m->f(m->conv0.b), m->has_cond ? p->cond_feat.as<float>() : nullptr,
+    launch_conv0(x, m->fblob.data() + m->conv0.w, m->fblob.data() + m->conv0.b, m->has_cond ? p->cond_feat.as<float>() : nullptr,
                  p->workspace.as<uint8_t>() + h0.offset, p->nb, p->nx, m->has_cond ? p->ncond : 1,
                  m->desc.x_channels, p->S, st);
     cudaEventRecord(ev[1], st);

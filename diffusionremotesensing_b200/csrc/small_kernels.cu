@@ -1,5 +1,6 @@
 // CUDA-core kernels around the tensor-core convolutions: condition encoder, conv0, time tables, DDPM update,
 // aggregation blend. Reference lines cited per kernel are relative to the reference checkout (see DESIGN.md for the map).
+#include <string.h>
 #include "small_kernels.cuh"
 
 #include <cuda_bf16.h>
@@ -124,79 +125,138 @@ int launch_bicubic_up(const float* in, float* out, int B, int C, int H, int W, i
 // ------------------------------------------------------------------------------------------------
 // conv0 + condition add -> bf16 NHWC (UNet_model_superres.py:342,355)
 // ------------------------------------------------------------------------------------------------
+// The 16 x Cx x 3 x 3 weights and the bias travel as a kernel parameter (constant bank), transposed to
+// [ci][ky][kx][co]: the FMAs take them as constant operands, so the load/store unit only sees the activations.
+// One warp = 128 consecutive pixels, lane l owns pixels l, l + 32, l + 64, l + 96 (every global access of the warp
+// is lane-contiguous); 64 accumulators per thread, updated with packed fp32x2 FMAs (two independent IEEE fp32 FMAs
+// per instruction: same rounding as fmaf, same (ci, ky, kx) summation order as the reference's direct convolution).
+// The condition feature is channel-planar fp32 [ncond, 16, S, S].
+struct Conv0Weights {
+  float w[4 * 9 * 16];
+  float b[16];
+};
+
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long v, unsigned long long w) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(v), "l"(w));
+}
+__device__ __forceinline__ unsigned long long pack2f(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+
+template <int CX>
 __global__ void __launch_bounds__(128)
-conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-             const float* __restrict__ cond, __nv_bfloat16* __restrict__ out, int nb, int nx, int ncond, int Cx, int S) {
-  // weights transposed to [ci][ky][kx][co] so the 16 output channels of one input tap are four 128-bit loads
-  __shared__ __align__(16) float sw[4 * 9 * 16];
-  __shared__ __align__(16) float sb[16];
-  for (int i = threadIdx.x; i < 16 * Cx * 9; i += blockDim.x) {
-    const int co = i / (Cx * 9), r = i % (Cx * 9);
-    sw[r * 16 + co] = w[i];
-  }
-  for (int i = threadIdx.x; i < 16; i += blockDim.x) sb[i] = bias[i];
-  __syncthreads();
-  const long long total = static_cast<long long>(nb) * S * S;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int px = static_cast<int>(idx % S);
-  const int py = static_cast<int>((idx / S) % S);
-  const int b = static_cast<int>(idx / (static_cast<long long>(S) * S));
-  float acc[16];
+conv0_kernel(const float* __restrict__ x, const __grid_constant__ Conv0Weights cw, const float* __restrict__ cond,
+             __nv_bfloat16* __restrict__ out, int nb, int nx, int ncond, int S) {
+  // the warp's 128 pixels x 16 channels of bf16 output (4 KiB, contiguous in global memory) are transposed through
+  // shared memory so that every global store instruction writes 512 contiguous bytes
+  __shared__ __align__(16) uint4 s_out[4][256];
+  const int S4 = S >> 2;
+  const long long total = static_cast<long long>(nb) * S * S4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long wbase = (static_cast<long long>(blockIdx.x) * 4 + warp) * 32;  // first pixel quad of this warp
+  const long long idx = wbase + lane;
+  const bool ok = idx < total;
+  const long long i2 = ok ? idx : 0;
+  const int px = static_cast<int>(i2 % S4) * 4;
+  const int py = static_cast<int>((i2 / S4) % S);
+  const int b = static_cast<int>(i2 / (static_cast<long long>(S4) * S));
+  const size_t plane = static_cast<size_t>(S) * S;
+  unsigned long long acc[4][8];  // [pixel][channel pair]
 #pragma unroll
-  for (int co = 0; co < 16; ++co) acc[co] = sb[co];
-  const int bx = b % nx;
-  for (int ci = 0; ci < Cx; ++ci) {
-    const float* ip = x + (static_cast<size_t>(bx) * Cx + ci) * S * S;
+  for (int c2 = 0; c2 < 8; ++c2) {
+    const unsigned long long b2 = pack2f(cw.b[2 * c2], cw.b[2 * c2 + 1]);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[p][c2] = b2;
+  }
+  const float* xin = x + static_cast<size_t>(b % nx) * CX * plane;
+#pragma unroll
+  for (int ci = 0; ci < CX; ++ci) {
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int yy = py + ky - 1;
-      const bool yok = (yy >= 0) && (yy < S);
+      float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ok && yy >= 0 && yy < S) {
+        const float* row = xin + ci * plane + static_cast<size_t>(yy) * S + px;
+        const float4 m = __ldg(reinterpret_cast<const float4*>(row));
+        v[1] = m.x; v[2] = m.y; v[3] = m.z; v[4] = m.w;
+        if (px > 0) v[0] = __ldg(row - 1);
+        if (px + 4 < S) v[5] = __ldg(row + 4);
+      }
+      unsigned long long vv[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) vv[i] = pack2f(v[i], v[i]);
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int xx = px + kx - 1;
-        const float v = (yok && xx >= 0 && xx < S) ? __ldg(ip + static_cast<size_t>(yy) * S + xx) : 0.f;
-        const float4* wp = reinterpret_cast<const float4*>(sw + ((ci * 3 + ky) * 3 + kx) * 16);
+        const float* wt = cw.w + ((ci * 3 + ky) * 3 + kx) * 16;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 w4 = wp[q];
-          acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+        for (int c2 = 0; c2 < 8; ++c2) {
+          const unsigned long long w2 = pack2f(wt[2 * c2], wt[2 * c2 + 1]);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) ffma2(acc[p][c2], vv[p + kx], w2);
         }
       }
     }
   }
-  if (cond) {
-    const float4* cp =
-        reinterpret_cast<const float4*>(cond + ((static_cast<size_t>(b % ncond) * S + py) * S + px) * 16);
+  float a[4][16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 c4 = __ldg(cp + q);
-      acc[4 * q + 0] += c4.x;
-      acc[4 * q + 1] += c4.y;
-      acc[4 * q + 2] += c4.z;
-      acc[4 * q + 3] += c4.w;
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c2 = 0; c2 < 8; ++c2) unpack2f(acc[p][c2], a[p][2 * c2], a[p][2 * c2 + 1]);
+  if (cond && ok) {
+    const float* cp = cond + static_cast<size_t>(b % ncond) * 16 * plane + static_cast<size_t>(py) * S + px;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(cp + c * plane));
+      a[0][c] += c4.x; a[1][c] += c4.y; a[2][c] += c4.z; a[3][c] += c4.w;
     }
   }
-  uint32_t pk[8];
+  // thread t owns bytes [128 t, 128 t + 128) of the warp's output: eight 16-byte chunks, XOR-swizzled by t & 7
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
-    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+  for (int p = 0; p < 4; ++p) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(a[p][2 * i], a[p][2 * i + 1]);
+      pk[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    s_out[warp][lane * 8 + ((2 * p) ^ (lane & 7))] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    s_out[warp][lane * 8 + ((2 * p + 1) ^ (lane & 7))] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
-  uint4* o = reinterpret_cast<uint4*>(out + static_cast<size_t>(idx) * 16);
-  o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  __syncwarp();
+  uint4* o = reinterpret_cast<uint4*>(out) + wbase * 8;  // 8 chunks per pixel quad
+  const long long chunks_left = (total - wbase) * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int t = 4 * k + (lane >> 3), c = lane & 7;
+    if (k * 32 + lane < chunks_left) o[k * 32 + lane] = s_out[warp][t * 8 + (c ^ (t & 7))];
+  }
 }
 
-int launch_conv0(const float* x, const float* w, const float* bias, const float* cond, void* out, int nb, int nx,
-                 int ncond, int Cx, int S, cudaStream_t s) {
-  if (Cx > 4) return static_cast<int>(cudaErrorInvalidValue);
+// w_host / bias_host: the fp32 parameters on the HOST ([16][Cx][3][3], [16]); cond: planar [ncond, 16, S, S] or null
+int launch_conv0(const float* x, const float* w_host, const float* bias_host, const float* cond, void* out, int nb,
+                 int nx, int ncond, int Cx, int S, cudaStream_t s) {
+  if (Cx < 1 || Cx > 4) return static_cast<int>(cudaErrorInvalidValue);
+  Conv0Weights cw;
+  memset(&cw, 0, sizeof(cw));
+  for (int co = 0; co < 16; ++co) {
+    for (int r = 0; r < Cx * 9; ++r) cw.w[r * 16 + co] = w_host[co * Cx * 9 + r];
+    cw.b[co] = bias_host[co];
+  }
+  if (S % 4) return static_cast<int>(cudaErrorInvalidValue);
   const long long total = static_cast<long long>(nb) * S * S;
-  conv0_kernel<<<cdiv(total, 128), 128, 0, s>>>(x, w, bias, cond, reinterpret_cast<__nv_bfloat16*>(out), nb, nx,
-                                                ncond, Cx, S);
+  const unsigned grid = static_cast<unsigned>(cdiv(total, 512));
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  switch (Cx) {
+    case 1: conv0_kernel<1><<<grid, 128, 0, s>>>(x, cw, cond, o, nb, nx, ncond, S); break;
+    case 2: conv0_kernel<2><<<grid, 128, 0, s>>>(x, cw, cond, o, nb, nx, ncond, S); break;
+    case 3: conv0_kernel<3><<<grid, 128, 0, s>>>(x, cw, cond, o, nb, nx, ncond, S); break;
+    default: conv0_kernel<4><<<grid, 128, 0, s>>>(x, cw, cond, o, nb, nx, ncond, S); break;
+  }
   return static_cast<int>(cudaGetLastError());
 }
 

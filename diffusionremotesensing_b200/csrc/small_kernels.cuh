@@ -14,9 +14,10 @@ int launch_conv3x3_small(const float* in, const float* w, const float* bias, con
 int launch_bicubic_up(const float* in, float* out, int B, int C, int H, int W, int k, cudaStream_t s);
 
 // conv0: h0[b,y,x,0:16] = bf16( conv3x3(x[b % nx])[0:16] + bias + cond[(b % ncond)] ), x fp32 NCHW [nx,Cx,S,S],
-// cond fp32 NHWC [ncond,S,S,16] or nullptr, out bf16 NHWC [nb,S,S,16].
-int launch_conv0(const float* x, const float* w, const float* bias, const float* cond, void* out, int nb, int nx,
-                 int ncond, int Cx, int S, cudaStream_t s);
+// cond fp32 channel-planar [ncond,16,S,S] or nullptr, out bf16 NHWC [nb,S,S,16]. w_host / bias_host are HOST pointers
+// ([16][Cx][3][3], [16]): the parameters are passed to the kernel by value (constant bank).
+int launch_conv0(const float* x, const float* w_host, const float* bias_host, const float* cond, void* out, int nb,
+                 int nx, int ncond, int Cx, int S, cudaStream_t s);
 
 // Sinusoidal time encoding (+ optional label embedding add): out[r, 0:100] for rows r < R.
 //   t: fp32 [R]; label: int32 [R] (-1 = none) or nullptr; emb: [num_classes,100] or nullptr.
