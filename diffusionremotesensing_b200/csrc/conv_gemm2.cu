@@ -47,14 +47,16 @@ struct RingPos {
 template <int NK>
 __device__ __forceinline__ void issue_resident(const Conv2Prog& prog, int kb, int cnt, uint32_t acc, uint32_t slot16,
                                                uint32_t b_base16) {
+  // the descriptor upper halves are constant over a sub-tile; the per-K-block part is one 128-bit load
+  const uint32_t a_hi = prog.kb[kb].a_hi, b_hi = prog.kb[kb].b_hi;
   for (int i = 0; i < cnt; ++i) {
-    const KB3 K = prog.kb[kb + i];
-    const uint32_t a_lo = K.a_lo + slot16;
-    const uint32_t b_lo = K.b_lo + b_base16;
-    const uint32_t d = acc + K.col;
-    umma_bf16_split(d, a_lo, K.a_hi, b_lo, K.b_hi, K.idesc, (K.flags & KB2_INIT) ? 0u : 1u);
+    const uint4 q = *reinterpret_cast<const uint4*>(&prog.kb[kb + i]);  // a_lo, b_lo, col | nk | flags, idesc
+    const uint32_t a_lo = q.x + slot16;
+    const uint32_t b_lo = q.y + b_base16;
+    const uint32_t d = acc + (q.z & 0xFFFFu);
+    umma_bf16_split(d, a_lo, a_hi, b_lo, b_hi, q.w, ((q.z >> 24) & KB2_INIT) ? 0u : 1u);
 #pragma unroll
-    for (int k = 1; k < NK; ++k) umma_bf16_split(d, a_lo + 2u * k, K.a_hi, b_lo + 2u * k, K.b_hi, K.idesc, 1u);
+    for (int k = 1; k < NK; ++k) umma_bf16_split(d, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, q.w, 1u);
   }
 }
 
@@ -122,6 +124,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem_base;
+  // Everything above (and the resident weight image below) only touches parameters that never change during
+  // sampling, so with a programmatic dependent launch it overlaps the tail of the previous layer.
+  griddep_launch();
 
   if (warp == kProducerWarp) {
     // ---- producer (whole warp walks the program, one elected lane issues) -------------------------
@@ -133,6 +138,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       }
     }
     __syncwarp();
+    griddep_wait();  // activations of the previous layer
     RingPos ar{0, 0}, br{0, 0};
     int pno = 0;
     for (int tile0 = first_tile; tile0 < a.n_tiles; tile0 += 2 * tile_step, ++pno) {
@@ -147,7 +153,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
         y0[p] = (t2 / a.tiles_x) * kTile2H;
         x0[p] = (t2 % a.tiles_x) * kTile2W;
       }
-      int st = 0;
+      int st = 0, sub_first = 0, sub_cnt = 0;
       TL(pno, 0);
       for (int kb = 0; kb < nkb; ++kb) {
         const KB3 K = prog.kb[kb];
@@ -168,14 +174,24 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
           }
         }
         if (!a.resident) {
-          mbar_wait(&s_bempty[br.idx], br.phase ^ 1u, a.err, 1);
-          if (elect_one()) {
-            mbar_expect_tx(&s_bfull[br.idx], K.b_bytes & 0xFFFFFFu);
-            bulk_load(b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes, w_image + K.b_off, K.b_bytes & 0xFFFFFFu,
-                      &s_bfull[br.idx]);
+          if (K.flags & KB2_FIRST) {
+            sub_first = kb;
+            sub_cnt = static_cast<int>(K.b_bytes >> 24);
           }
-          __syncwarp();
-          br.advance(a.b_stages);
+          if ((kb - sub_first) % a.b_unit == 0) {
+            // one ring stage = the next (up to) b_unit weight tiles of this sub-tile, contiguous in the image
+            const uint32_t tile_pad = ((K.b_bytes & 0xFFFFFFu) + 1023u) & ~1023u;
+            const uint32_t bytes = static_cast<uint32_t>(min(a.b_unit, sub_first + sub_cnt - kb)) * tile_pad;
+            mbar_wait(&s_bempty[br.idx], br.phase ^ 1u, a.err, 1);
+            if (elect_one()) {
+              mbar_expect_tx(&s_bfull[br.idx], bytes);
+              uint8_t* dst = b_base + static_cast<size_t>(br.idx) * a.b_stage_bytes;
+              for (uint32_t off = 0; off < bytes; off += 16384u)
+                bulk_load(dst + off, w_image + K.b_off + off, min(16384u, bytes - off), &s_bfull[br.idx]);
+            }
+            __syncwarp();
+            br.advance(a.b_stages);
+          }
         }
       }
       TL(pno, 1);
@@ -211,50 +227,45 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
         const KB3 K0 = prog.kb[kb];
         const int cnt = static_cast<int>(K0.b_bytes >> 24);  // K-blocks that read this sub-tile
         const bool leader = elect_one();
+        const int n_units = a.resident ? 0 : (cnt + a.b_unit - 1) / a.b_unit;
         if (leader) {
-          if (valid && a.resident) {
+          if (a.resident) {
             // hot path: counted loop, K = 16 slice count fixed per sub-tile, no data-dependent branch
-            const uint32_t bofs = b_base16;
-            if (K0.nk == 4)
-              issue_resident<4>(prog, kb, cnt, acc, slot16, bofs);
-            else if (K0.nk == 2)
-              issue_resident<2>(prog, kb, cnt, acc, slot16, bofs);
-            else
-              issue_resident<1>(prog, kb, cnt, acc, slot16, bofs);
+            if (valid) {
+              if (K0.nk == 4)
+                issue_resident<4>(prog, kb, cnt, acc, slot16, b_base16);
+              else if (K0.nk == 2)
+                issue_resident<2>(prog, kb, cnt, acc, slot16, b_base16);
+              else
+                issue_resident<1>(prog, kb, cnt, acc, slot16, b_base16);
+            }
           } else {
-            for (int i = 0; i < cnt; ++i) {
-              const KB3 K = prog.kb[kb + i];
-              uint32_t b_lo = K.b_lo + b_base16;
-              if (!a.resident) {
-                mbar_wait(&s_bfull[br.idx], br.phase, a.err, 2);
-                tc_fence_after();
-                b_lo = 0x10000u + b_base16 + static_cast<uint32_t>((br.idx * a.b_stage_bytes) >> 4);
-              }
+            // streamed weights: one ring stage per unit of up to b_unit K-blocks (b_lo = offset inside the unit)
+            for (int u0 = 0; u0 < cnt; u0 += a.b_unit) {
+              const int nu = min(a.b_unit, cnt - u0);
+              mbar_wait(&s_bfull[br.idx], br.phase, a.err, 2);
+              tc_fence_after();
               if (valid) {
-                const uint32_t a_lo = K.a_lo + slot16;
-                const uint32_t d = acc + K.col;
-                umma_bf16_split(d, a_lo, K.a_hi, b_lo, K.b_hi, K.idesc, (K.flags & KB2_INIT) ? 0u : 1u);
-                if (K.nk >= 2) umma_bf16_split(d, a_lo + 2u, K.a_hi, b_lo + 2u, K.b_hi, K.idesc, 1u);
-                if (K.nk == 4) {
-                  umma_bf16_split(d, a_lo + 4u, K.a_hi, b_lo + 4u, K.b_hi, K.idesc, 1u);
-                  umma_bf16_split(d, a_lo + 6u, K.a_hi, b_lo + 6u, K.b_hi, K.idesc, 1u);
-                }
-              }
-              if (!a.resident) {
-                if (valid)
-                  umma_commit(&s_bempty[br.idx]);
+                const uint32_t bofs = b_base16 + static_cast<uint32_t>((br.idx * a.b_stage_bytes) >> 4);
+                if (K0.nk == 4)
+                  issue_resident<4>(prog, kb + u0, nu, acc, slot16, bofs);
+                else if (K0.nk == 2)
+                  issue_resident<2>(prog, kb + u0, nu, acc, slot16, bofs);
                 else
-                  mbar_arrive(&s_bempty[br.idx]);  // no tile 1 in the last pair: release the stage unused
-                br.advance(a.b_stages);
+                  issue_resident<1>(prog, kb + u0, nu, acc, slot16, bofs);
+                umma_commit(&s_bempty[br.idx]);
+              } else {
+                mbar_arrive(&s_bempty[br.idx]);  // no tile 1 in the last pair: release the stage unused
               }
+              br.advance(a.b_stages);
             }
           }
           if (valid) umma_commit(&s_aempty[ar.idx]);
         }
         const int kb_end = kb + cnt;
         __syncwarp();
-        if (!a.resident && !leader)
-          for (int i = kb; i < kb_end; ++i) br.advance(a.b_stages);
+        if (!leader)
+          for (int i = 0; i < n_units; ++i) br.advance(a.b_stages);
         kb = kb_end;
         ar.advance(a.a_slots);
         ar.advance(a.a_slots);
@@ -266,6 +277,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     }
   } else {
     // ---- epilogue group p: tile p of every pair ----------------------------------------------------------
+    griddep_wait();  // gate maps / state read by the epilogue, and write-after-read on the output tensor
     const int p = warp >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -379,17 +391,31 @@ int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& 
   static const bool generic = (getenv("DRS_V2_GENERIC_EPILOGUE") != nullptr);
   const int fl = (epi_kind == EPI_STD && !generic) ? args.epi.flags : -1;
   bool done = false;
+  static const bool no_pdl = (getenv("DRS_V2_NO_PDL") != nullptr);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = g;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaError_t err = cudaSuccess;
 #define X(EPI, FL)                                                                                      \
   if (!done && epi_kind == EPI && fl == (FL)) {                                                         \
-    conv_gemm2_kernel<EPI, (FL)><<<g, block, smem_bytes, stream>>>(map0, map1, map_out, args, prog);    \
+    err = cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<EPI, (FL)>, map0, map1, map_out, args, prog);      \
     done = true;                                                                                        \
   }
   DRS_GEMM2_VARIANTS(X)
 #undef X
   if (!done) {
     if (epi_kind != EPI_STD) return static_cast<int>(cudaErrorInvalidValue);
-    conv_gemm2_kernel<EPI_STD, -1><<<g, block, smem_bytes, stream>>>(map0, map1, map_out, args, prog);
+    err = cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<EPI_STD, -1>, map0, map1, map_out, args, prog);
   }
+  if (err != cudaSuccess) return static_cast<int>(err);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -24,17 +24,19 @@ constexpr int kTile2H = 16;   // row groups per M = 128 tile
 constexpr int kGemm2Threads = 352;  // 8 epilogue warps + 2 MMA issuers + 1 producer
 constexpr int kMaxSubTiles = 16;
 constexpr int kMaxASlots = 8;
-constexpr int kMaxBStages = 8;
+constexpr int kMaxBStages = 16;
 
 struct __align__(16) KB3 {  // one K-block = one filter tap of one channel block: nk MMAs of K = 16
+  // first 16 bytes: everything the issuing lane needs per K-block (one 128-bit uniform load)
   uint32_t a_lo;      // lower half of the A descriptor relative to the A slot: (tap offset / 16) | LBO field
-  uint32_t a_hi;      // upper half of the A descriptor (SBO = halo row pitch, version, swizzle mode)
-  uint32_t b_lo;      // lower half of the B descriptor relative to the weight region: (tile offset / 16) | LBO field
-  uint32_t b_hi;      // upper half of the B descriptor
-  uint32_t idesc;     // tcgen05 instruction descriptor (M = 128, N, bf16 x bf16 -> fp32)
+  uint32_t b_lo;      // lower half of the B descriptor relative to the weight region / ring stage | LBO field
   uint16_t col;       // accumulator column offset inside one TMEM buffer
   uint8_t nk;         // K = 16 slices (ck / 16)
   uint8_t flags;      // KB2_*
+  uint32_t idesc;     // tcgen05 instruction descriptor (M = 128, N, bf16 x bf16 -> fp32)
+  // second 16 bytes: constant over a sub-tile (descriptor upper halves) or used by the producer only
+  uint32_t a_hi;      // upper half of the A descriptor (SBO = halo row pitch, version, swizzle mode)
+  uint32_t b_hi;      // upper half of the B descriptor
   uint32_t b_off;     // byte offset of the weight tile inside one split's image (tiles are 1 KiB aligned)
   uint32_t b_bytes;   // bits 0..23: weight tile bytes (n * ck * 2); bits 24..31 (FIRST record): K-blocks of the sub-tile
 };
@@ -79,6 +81,7 @@ struct Conv2Args {
   int tiles_x, tiles_y, n_tiles;
   int a_slots, a_slot_bytes;
   int b_stages, b_stage_bytes;
+  int b_unit;               // streamed weights: K-blocks per ring stage (units never straddle sub-tiles)
   int tmem_cols;            // allocation (power of two)
   int acc_cols;             // columns one tile's accumulators use
   int acc_bufs;             // 1 or 2

@@ -99,6 +99,7 @@ struct GemmSpec {
     Conv2Prog prog;                   // K-block / sub-tile program, passed to the kernel by value
     int halo_w[2] = {0, 0}, halo_h[2] = {0, 0}, npy[2] = {1, 1};   // TMA box geometry per source
     int a_slot_bytes = 0, b_stage_bytes = 0;
+    int b_unit = 1;                   // streamed weights: K-blocks per ring stage
     int acc_cols = 0;
     uint32_t w_split_off = 0, w_split_bytes = 0;
   } v2;

@@ -290,9 +290,13 @@ struct Builder {
     }
     if (n_kb > kMaxKBlocks || n_st > kMaxSubTiles) return;
     v.a_slot_bytes = (max_a + 1023) & ~1023;
-    v.b_stage_bytes = (max_b + 1023) & ~1023;
     // resident when the split's image plus two A slots leaves a CTA within ~200 KB
     v.resident = (w_image + 2 * static_cast<size_t>(v.a_slot_bytes) <= 200 * 1024);
+    // Streamed weights travel in units of up to b_unit consecutive K-blocks of one sub-tile (<= 32 KiB): one bulk
+    // copy, one full / empty barrier round trip and one tcgen05.commit per unit instead of per K-block.
+    const int tile_pad = (max_b + 1023) & ~1023;
+    v.b_unit = std::max(1, std::min(4, (32 * 1024) / tile_pad));
+    v.b_stage_bytes = v.resident ? tile_pad : v.b_unit * tile_pad;
     v.w_split_bytes = static_cast<uint32_t>(w_image);
     while (m->wblob.size() % 1024) m->wblob.push_back(0);
     v.w_split_off = static_cast<uint32_t>(m->wblob.size());
@@ -385,6 +389,17 @@ struct Builder {
       int cnt = 1;
       while (!(P.kb[i + cnt - 1].flags & KB2_LAST)) ++cnt;
       P.kb[i].b_bytes |= static_cast<uint32_t>(cnt) << 24;
+    }
+    if (!v.resident) {
+      // streamed mode: b_lo = offset of the tile inside its unit (the issuing lane adds the ring stage)
+      for (int i = 0; i < v.nkb;) {
+        const int cnt = static_cast<int>(P.kb[i].b_bytes >> 24);
+        for (int j = 0; j < cnt; ++j) {
+          const int first = i + (j / v.b_unit) * v.b_unit;
+          P.kb[i + j].b_lo = static_cast<uint32_t>((P.kb[i + j].b_off - P.kb[first].b_off) / 16) | 0x10000u;
+        }
+        i += cnt;
+      }
     }
     v.acc_cols = max_col;
     v.usable = true;

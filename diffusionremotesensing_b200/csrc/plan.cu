@@ -213,6 +213,7 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   a.n_tiles = a.tiles_x * a.tiles_y * p->nb;
   a.a_slot_bytes = v.a_slot_bytes;
   a.b_stage_bytes = v.b_stage_bytes;
+  a.b_unit = v.b_unit;
   a.acc_cols = v.acc_cols;
   if (2 * v.acc_cols > 512) return DRS_OK;  // the kernel keeps one accumulator per tile of a pair in TMEM
   // two accumulator buffers per tile of the pair when TMEM allows: the epilogue of pair i overlaps the MMAs of i + 1
@@ -233,7 +234,8 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   // (sub-tile, tile-of-pair) and every slot is released after its own taps, so two slots per sub-tile in flight plus
   // two of prefetch keep both issuers fed.
   const int spt = a.n_sub_tiles;
-  a.b_stages = a.resident ? 1 : std::min(4, v.nkb);
+  static const int b_stage_knob = getenv("DRS_V2_BSTAGES") ? atoi(getenv("DRS_V2_BSTAGES")) : 3;
+  a.b_stages = a.resident ? 1 : std::min(std::min(b_stage_knob, kMaxBStages), v.nkb);
   const int b_bytes = a.resident ? static_cast<int>(v.w_split_bytes) : a.b_stages * v.b_stage_bytes;
   const int want_slots = std::min(kMaxASlots, std::max(4, 2 * spt + 2));
   // Staged TMA-store epilogue (EPI_STD, bf16 NHWC output whose tiles never straddle two images): 4 KiB per

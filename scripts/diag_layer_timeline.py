@@ -37,3 +37,11 @@ if any(tr):
         row = tr[c * 4:c * 4 + 4]
         if any(row):
             print(f"  chunk {c:2d}: " + " ".join(f"{(v - base) if v else -1:7d}" for v in row))
+it = [buf[256 + 32 + i] for i in range(30)]
+if any(it):
+    base = min(v for v in it if v > 0)
+    print("issuer 0 trace, pair 3 (per K-block: start, after B wait + MMA issue, after commit):")
+    for k in range(10):
+        row = it[k * 3:k * 3 + 3]
+        if any(row):
+            print(f"  kb {k:2d}: " + " ".join(f"{(v - base) if v else -1:7d}" for v in row))
