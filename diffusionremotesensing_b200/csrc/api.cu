@@ -140,8 +140,8 @@ int drs_ddpm_update(float* x_dev, const float* eps_dev, const float* noise_dev_o
   cudaStream_t st = as_stream(stream);
   DRS_CUDA(cudaMemcpyAsync(dev, &h, sizeof(Tmp), cudaMemcpyHostToDevice, st));
   const float* coef = reinterpret_cast<const float*>(dev);
-  const int* step = reinterpret_cast<const int*>(reinterpret_cast<const char*>(dev) + offsetof(Tmp, step));
-  DRS_CUDA(static_cast<cudaError_t>(launch_ddpm_update(x_dev, eps_dev, noise_dev_or_null, coef, step, numel, 0, 0.f, st)));
+  int* step = reinterpret_cast<int*>(reinterpret_cast<char*>(dev) + offsetof(Tmp, step));
+  DRS_CUDA(static_cast<cudaError_t>(launch_ddpm_update(x_dev, eps_dev, noise_dev_or_null, coef, step, numel, 0, 0.f, nullptr, 0, 0, nullptr, st)));
   DRS_CUDA(cudaStreamSynchronize(st));  // `h` is a stack temporary
   return DRS_OK;
 }

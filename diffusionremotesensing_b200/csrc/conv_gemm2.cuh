@@ -23,7 +23,7 @@ constexpr int kTile2W = 8;    // pixels per accumulator row group (fixed by the 
 constexpr int kTile2H = 16;   // row groups per M = 128 tile
 constexpr int kGemm2Threads = 352;  // 8 epilogue warps + 2 MMA issuers + 1 producer
 constexpr int kMaxSubTiles = 16;
-constexpr int kMaxASlots = 8;
+constexpr int kMaxASlots = 16;
 constexpr int kMaxBStages = 16;
 
 struct __align__(16) KB3 {  // one K-block = one filter tap of one channel block: nk MMAs of K = 16

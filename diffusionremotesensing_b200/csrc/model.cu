@@ -165,7 +165,23 @@ struct Builder {
       std::set<int> seen;
       int count = 0;
       for (const ConvTerm& t : terms) {
-        const int ck = t.C >= 64 ? 64 : t.C;
+        int ck = t.C >= 64 ? 64 : t.C;
+        {
+          // experiment knob: DRS_CK32=<comma separated name fragments> halves the channel block (and the A slot) of
+          // the named layers so that twice as many halo tiles are in flight
+          static const char* const ck32 = getenv("DRS_CK32");
+          if (ck32 && ck == 64) {
+            std::string list(ck32);
+            size_t pos = 0;
+            while (pos <= list.size()) {
+              const size_t e = list.find(',', pos);
+              const std::string frag = list.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+              if (!frag.empty() && g.name.find(frag) != std::string::npos) ck = 32;
+              if (e == std::string::npos) break;
+              pos = e + 1;
+            }
+          }
+        }
         if (ck != 16 && ck != 32 && ck != 64) {
           set_error("%s: unsupported source channel count %d", g.name.c_str(), t.C);
           return false;

@@ -738,9 +738,10 @@ static int enqueue_step(DrsPlan* p, bool with_noise, cudaStream_t st) {
   DRS_TRY(enqueue_forward(p, p->x, p->eps, st));
   const size_t numel = static_cast<size_t>(p->nx) * m->desc.out_channels * p->S * p->S;
   const int cfg = (p->nb == 2 * p->nx) ? 1 : 0;
+  // posterior update + sampler bookkeeping (step index and time-table rows) in one launch
   DRS_CUDA(static_cast<cudaError_t>(launch_ddpm_update(p->x, p->eps, with_noise ? p->noise : nullptr, p->d_coef,
-                                                       p->d_step, numel, cfg, p->cfg_scale, st)));
-  DRS_CUDA(static_cast<cudaError_t>(launch_advance(p->d_trow, p->nb, p->n_uniq, p->d_step, st)));
+                                                       p->d_step, numel, cfg, p->cfg_scale, p->d_trow, p->nb,
+                                                       p->n_uniq, p->d_step + 1, st)));
   return DRS_OK;
 }
 
@@ -798,7 +799,7 @@ int debug_bind_and_run(DrsPlan* p, const void* in, int gridW, int gridH, int src
   return DRS_OK;
 }
 
-int launches_per_step(const DrsPlan* p) { return static_cast<int>(p->launches.size()) + 3; }
+int launches_per_step(const DrsPlan* p) { return static_cast<int>(p->launches.size()) + 2; }
 
 // ------------------------------------------------------------------------------------------------
 // per-launch accounting (bench / profiles): algorithmic work and live CUDA-event timing

@@ -1,5 +1,6 @@
 // CUDA-core kernels around the tensor-core convolutions: condition encoder, conv0, time tables, DDPM update,
 // aggregation blend. Reference lines cited per kernel are relative to the reference checkout (see DESIGN.md for the map).
+#include <stdlib.h>
 #include <string.h>
 #include "small_kernels.cuh"
 
@@ -7,6 +8,9 @@
 #include <math.h>
 
 namespace drs {
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args);
 
 static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
@@ -155,6 +159,8 @@ conv0_kernel(const float* __restrict__ x, const __grid_constant__ Conv0Weights c
   // the warp's 128 pixels x 16 channels of bf16 output (4 KiB, contiguous in global memory) are transposed through
   // shared memory so that every global store instruction writes 512 contiguous bytes
   __shared__ __align__(16) uint4 s_out[4][256];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int S4 = S >> 2;
   const long long total = static_cast<long long>(nb) * S * S4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -251,12 +257,14 @@ int launch_conv0(const float* x, const float* w_host, const float* bias_host, co
   const long long total = static_cast<long long>(nb) * S * S;
   const unsigned grid = static_cast<unsigned>(cdiv(total, 512));
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  cudaError_t e;
   switch (Cx) {
-    case 1: conv0_kernel<1><<<grid, 128, 0, s>>>(x, cw, cond, o, nb, nx, ncond, S); break;
-    case 2: conv0_kernel<2><<<grid, 128, 0, s>>>(x, cw, cond, o, nb, nx, ncond, S); break;
-    case 3: conv0_kernel<3><<<grid, 128, 0, s>>>(x, cw, cond, o, nb, nx, ncond, S); break;
-    default: conv0_kernel<4><<<grid, 128, 0, s>>>(x, cw, cond, o, nb, nx, ncond, S); break;
+    case 1: e = launch_pdl(conv0_kernel<1>, dim3(grid), dim3(128), s, x, cw, cond, o, nb, nx, ncond, S); break;
+    case 2: e = launch_pdl(conv0_kernel<2>, dim3(grid), dim3(128), s, x, cw, cond, o, nb, nx, ncond, S); break;
+    case 3: e = launch_pdl(conv0_kernel<3>, dim3(grid), dim3(128), s, x, cw, cond, o, nb, nx, ncond, S); break;
+    default: e = launch_pdl(conv0_kernel<4>, dim3(grid), dim3(128), s, x, cw, cond, o, nb, nx, ncond, S); break;
   }
+  if (e != cudaSuccess) return static_cast<int>(e);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -359,10 +367,16 @@ __device__ __forceinline__ float lerp_aten(float u, float c, float w) {
   return (fabsf(w) < 0.5f) ? __fadd_rn(u, __fmul_rn(w, d)) : __fsub_rn(c, __fmul_rn(d, __fsub_rn(1.f, w)));
 }
 
+// trow / counter (optional): sampler bookkeeping folded into this launch. Every block reads *step before it does
+// anything else and bumps `counter` when it is done, so the block that brings the count to gridDim.x knows that nobody
+// still needs the old value: it decrements the step index and the time-table rows and re-arms the counter.
 __global__ void ddpm_update_kernel(float* __restrict__ x, const float* __restrict__ eps,
-                                   const float* __restrict__ noise, const float* __restrict__ coef,
-                                   const int* __restrict__ step, size_t n4, int cfg, float cfg_scale) {
-  const float4 cf = __ldg(reinterpret_cast<const float4*>(coef) + __ldg(step));
+                                   const float* __restrict__ noise, const float* __restrict__ coef, int* step,
+                                   size_t n4, int cfg, float cfg_scale, int* trow, int n_rows, int row_dec,
+                                   int* counter) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const float4 cf = __ldg(reinterpret_cast<const float4*>(coef) + *reinterpret_cast<volatile int*>(step));
   const bool has_z = (noise != nullptr) && (cf.z != 0.f || true);
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -383,15 +397,51 @@ __global__ void ddpm_update_kernel(float* __restrict__ x, const float* __restric
     xv.w = ddpm_one(xv.w, ev.w, zv.w, cf.x, cf.y, cf.z, has_z);
     reinterpret_cast<float4*>(x)[i] = xv;
   }
+  if (trow) {
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const int done = atomicAdd(counter, 1);
+      s_last = (done == static_cast<int>(gridDim.x) - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      for (int i = threadIdx.x; i < n_rows; i += blockDim.x) trow[i] -= row_dec;
+      if (threadIdx.x == 0) {
+        *step -= 1;
+        *counter = 0;
+      }
+    }
+  }
 }
 
-int launch_ddpm_update(float* x, const float* eps, const float* noise, const float* coef, const int* step,
-                       size_t numel, int cfg, float cfg_scale, cudaStream_t s) {
+// Launch helper: programmatic dependent launch (the kernel's griddepcontrol.wait orders it after its predecessor).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
+  static const bool no_pdl = (getenv("DRS_V2_NO_PDL") != nullptr);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+int launch_ddpm_update(float* x, const float* eps, const float* noise, const float* coef, int* step, size_t numel,
+                       int cfg, float cfg_scale, int* trow, int n_rows, int row_dec, int* counter, cudaStream_t s) {
   if (numel % 4) return static_cast<int>(cudaErrorInvalidValue);
   const size_t n4 = numel / 4;
   int blocks = cdiv(static_cast<long long>(n4), 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  ddpm_update_kernel<<<blocks, 256, 0, s>>>(x, eps, noise, coef, step, n4, cfg, cfg_scale);
+  const cudaError_t e = launch_pdl(ddpm_update_kernel, dim3(blocks), dim3(256), s, x, eps, noise, coef, step, n4, cfg,
+                                   cfg_scale, trow, n_rows, row_dec, counter);
+  if (e != cudaSuccess) return static_cast<int>(e);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -30,8 +30,8 @@ int launch_sgemm_nt(const float* A, int lda, const float* B, int ldb, const floa
 
 // x <- c1 * (x - c2 * eps) + c3 * z, coefficient row picked by *step; reference rounding order (no FMA).
 //   cfg != 0: eps = lerp(eps_u, eps_c, cfg_scale) with eps_c = eps[0:numel], eps_u = eps[numel:2 numel] (ATen lerp form).
-int launch_ddpm_update(float* x, const float* eps, const float* noise, const float* coef, const int* step,
-                       size_t numel, int cfg, float cfg_scale, cudaStream_t s);
+int launch_ddpm_update(float* x, const float* eps, const float* noise, const float* coef, int* step, size_t numel,
+                       int cfg, float cfg_scale, int* trow, int n_rows, int row_dec, int* counter, cudaStream_t s);
 
 // out = sa[b] * x + sb[b] * eps per sample b (forward noising), fp32, separately rounded multiply / add.
 int launch_noise_images(const float* x, const float* eps, const float* sa, const float* sb, float* out, int n,

@@ -26,9 +26,20 @@ t0 = buf[0]
 names = ["p_start", "p_issued", "m_tmemfree", "m_afull", "m_issued", "e_tfull", "e_done", "m1_issued"]
 print(os.environ.get("DRS_V2_TIMELINE_LAYER"), "total ms", float(ms.sum()))
 print("pair " + " ".join(f"{nm:>10s}" for nm in names))
-for t in range(16):
+npairs = int(os.environ.get("DRS_TL_PAIRS", "16"))
+last = 0
+for t in range(min(npairs, 32)):
     if buf[t * 8] == 0 and t > 0: break
     print(f"{t:4d} " + " ".join(f"{buf[t * 8 + s] - t0:10d}" for s in range(8)))
+    last = max(last, buf[t * 8 + 6] - t0)
+name = os.environ.get("DRS_V2_TIMELINE_LAYER")
+import ctypes
+nm = ctypes.create_string_buffer(64)
+for i in range(nl):
+    lib.drs_plan_launch_info(plan, i, nm, 64, None, None, None, None)
+    if name and name in nm.value.decode():
+        print(f"launch {nm.value.decode()}: event time {float(ms[i]) * 1000:.1f} us; CTA 0 recorded span {last} cycles "
+              f"= {last / 1.965e3:.1f} us at 1965 MHz")
 tr = [buf[256 + i] for i in range(64)]
 if any(tr):
     base = min(v for v in tr if v > 0)

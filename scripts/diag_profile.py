@@ -25,3 +25,9 @@ for r in range(reps):
     except Exception as e:
         print("rep", r, "FAILED", e)
         break
+import ctypes
+nm = ctypes.create_string_buffer(64)
+print("per-launch ms (last rep):")
+for i in range(nl):
+    lib.drs_plan_launch_info(plan, i, nm, 64, None, None, None, None)
+    print(f"  {nm.value.decode():28s} {float(ms[i]) * 1000:8.1f} us")
