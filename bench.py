@@ -13,8 +13,10 @@ its own GPU (weak scaling, no data-path collective).
   e2e        the same metric through the public API, Diffusion.sample(n, model, lr_img) with noise_steps = K + 1,
              from pinned host tensors to a host result: H2D of lr_img and x_T, condition encode, time-table
              preparation, K graph-replayed steps, D2H of the samples -- all inside the timed region
-  roofline   tensor-core bound: algorithmic conv FLOPs of one UNet evaluation / summed CUDA-event time of the
-             tcgen05 implicit-GEMM launches (drs_plan_profile), against MEASURED_PEAKS.json bf16_tflops_sustained
+  roofline   tensor-core bound: algorithmic conv FLOPs of one UNet evaluation / CUDA-event time of the chain of
+             tcgen05 implicit-GEMM launches of one forward (drs_plan_time_forward: events around the chain on the
+             launching stream), against MEASURED_PEAKS.json bf16_tflops_sustained; `traffic` = DRAM bytes per launch
+             from the committed ncu capture (profiles/ncu_traffic.json)
   cpu_baseline  the reference algorithm (oracle port: the same torch CPU ops the reference's modules call) timed on
              this box's host cores on a bounded sample of the same workload
 
@@ -58,21 +60,34 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons. The sampler is started before the warm-up (nvidia-smi needs a few hundred
+    milliseconds to produce its first line) and the samples are filtered to the timed region by their timestamps."""
 
     def __init__(self, index):
         self.proc = None
         self.path = os.path.join("/tmp", f"drs_clocks_{os.getpid()}.csv")
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.f = open(self.path, "w")
+            self.f = open(self.path, "w", buffering=1)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def wait_first(self, timeout=3.0):
+        """Blocks until nvidia-smi has produced its first line (it needs a few hundred milliseconds to start)."""
+        t0 = time.time()
+        while self.proc is not None and time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                pass
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
@@ -82,22 +97,29 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in open(self.path):
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 6:
+            if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]),
+                             {n for n, v in zip(names, parts[3:7]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        window = "timed region"
+        sel = [r for r in rows if t_begin is not None and t_begin <= r[0] <= t_end]
+        if not sel:
+            # region shorter than the sampling period: fall back to every sample taken under load (warm-up included)
+            sel, window = rows, "whole run (timed region shorter than the sampling period)"
+        if sel:
+            reasons = set()
+            for r in sel:
+                reasons |= r[3]
+            out = {"sm_mhz": statistics.median([r[1] for r in sel]), "sm_max_mhz": max(r[2] for r in sel),
+                   "reasons": sorted(reasons), "samples": len(sel), "window": window}
         try:
             os.remove(self.path)
         except OSError:
@@ -218,26 +240,30 @@ def run_ours(args):
         z.normal_()
         N.check(lib.drs_sampler_step(plan, 1, st))
 
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.wait_first()
     for _ in range(W):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record()
     for _ in range(K):
         step()
     e1.record()
     torch.cuda.synchronize()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
     N.check(lib.drs_plan_check(plan, st))
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
-    clock_info = clocks.stop() if clocks else None
+    clock_info = clocks.stop(t_begin, t_end) if clocks else None
     launches_per_step = lib.drs_sampler_launches_per_step(plan)
     value = world * BATCH * K / (ms * 1e-3)
 
@@ -262,12 +288,30 @@ def run_ours(args):
                 tot_f += fl.value
                 tot_ms += float(ms_out[i])
         peaks = measured_peaks()
-        achieved = tot_f / (tot_ms * 1e-3) / 1e12
+        # duration of the tensor-core launches as the sampler runs them: CUDA events around the whole chain of one
+        # forward on the launching stream (no event between launches, gate branch on its side stream)
+        ms2 = torch.zeros(2, dtype=torch.float32)
+        N.check(lib.drs_plan_time_forward(plan, N.ptr(x), N.ptr(eps), max(5, min(K, 20)), N.ptr(ms2), st))
+        N.check(lib.drs_plan_check(plan, st))
+        chain_ms = float(ms2[1])
+        n_conv = n_l - 1
+        achieved = tot_f / (chain_ms * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
-                    "kernel": "conv_gemm_kernel (all tcgen05 implicit-GEMM launches of one UNet evaluation)",
-                    "algorithmic_gflop_per_eval": tot_f / 1e9, "kernel_ms_per_eval": tot_ms,
-                    "kernel_share_of_step": tot_ms / (ms / K)}
+                    "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peaks["source"],
+                    "kernel": f"conv_gemm2_kernel (the {n_conv} tcgen05 implicit-GEMM launches of one UNet evaluation)",
+                    "launches_per_eval": n_conv,
+                    "algorithmic_gflop_per_eval": tot_f / 1e9, "algorithmic_gflop_per_launch": tot_f / 1e9 / n_conv,
+                    "kernel_ms_per_eval": chain_ms, "kernel_ms_per_launch": chain_ms / n_conv,
+                    "conv0_ms": float(ms2[0]),
+                    "kernel_share_of_step": chain_ms / (ms / K),
+                    "per_launch_event_sum_ms": tot_ms}
         if args.layers:
             with open(args.layers, "w") as f:
                 json.dump(layer_rows, f, indent=1)

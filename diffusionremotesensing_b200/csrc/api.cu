@@ -25,6 +25,7 @@ int launches_per_step(const DrsPlan*);
 int launch_count(const DrsPlan*);
 int launch_info(const DrsPlan*, int, char*, int, double*, double*, int*, int*);
 int plan_profile(DrsPlan*, const float*, float*, int, float*, cudaStream_t);
+int plan_time_forward(DrsPlan*, const float*, float*, int, float*, cudaStream_t);
 int mma_rate(int, int, int, int, long long*);
 int mma_rate2(int, int, int, int, int, int, int, long long*);
 int debug_bind_and_run(DrsPlan*, const void*, int, int, int, int, void*, int, int, cudaStream_t);
@@ -120,6 +121,13 @@ int drs_plan_profile(DrsPlan* p, const float* x_dev, float* eps_dev, int iters, 
     return DRS_E_INVALID;
   }
   return plan_profile(p, x_dev, eps_dev, iters, ms_out, as_stream(stream));
+}
+int drs_plan_time_forward(DrsPlan* p, const float* x_dev, float* eps_dev, int iters, float* ms_out2, void* stream) {
+  if (!p) {
+    set_error("null plan");
+    return DRS_E_INVALID;
+  }
+  return plan_time_forward(p, x_dev, eps_dev, iters, ms_out2, as_stream(stream));
 }
 
 int drs_ddpm_update(float* x_dev, const float* eps_dev, const float* noise_dev_or_null, float c1, float c2, float c3,

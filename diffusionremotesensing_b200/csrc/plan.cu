@@ -567,13 +567,15 @@ int time_embed(DrsPlan* p, const float* t_dev, const int* label_dev, cudaStream_
 // ------------------------------------------------------------------------------------------------
 // UNet forward
 // ------------------------------------------------------------------------------------------------
-static int enqueue_forward(DrsPlan* p, const float* x, float* eps, cudaStream_t st) {
+static int enqueue_forward(DrsPlan* p, const float* x, float* eps, cudaStream_t st, cudaEvent_t* tev = nullptr) {
   const DrsModel* m = p->m;
   const ActTensor& h0 = p->acts.at("h0");
+  if (tev) DRS_CUDA(cudaEventRecord(tev[0], st));
   DRS_CUDA(static_cast<cudaError_t>(launch_conv0(x, m->fblob.data() + m->conv0.w, m->fblob.data() + m->conv0.b,
                                                  m->has_cond ? p->cond_feat.as<float>() : nullptr,
                                                  p->workspace.as<uint8_t>() + h0.offset, p->nb, p->nx,
                                                  m->has_cond ? p->ncond : 1, m->desc.x_channels, p->S, st)));
+  if (tev) DRS_CUDA(cudaEventRecord(tev[1], st));
   // Decoder stage i: [gating -> psi -> attention result] only meets [UpConvBlock conv -> transposed conv] at
   // up_convs.i, so the gate branch runs on a side stream (forked / joined with events; inside a CUDA-graph capture
   // this becomes two parallel branches of the graph). The gate kernels are small and latency-bound.
@@ -611,7 +613,40 @@ static int enqueue_forward(DrsPlan* p, const float* x, float* eps, cudaStream_t 
       return DRS_E_CUDA;
     }
   }
+  if (tev) DRS_CUDA(cudaEventRecord(tev[2], st));
   return DRS_OK;
+}
+
+// Live timing of the forward as the sampler runs it (same launch sequence, side-stream gate branch included):
+// ms_out[0] = conv0, ms_out[1] = the chain of tensor-core launches (first launch to completion of the last one, no
+// events in between), averaged over `iters` forwards.
+int plan_time_forward(DrsPlan* p, const float* x, float* eps, int iters, float* ms_out, cudaStream_t st) {
+  if (!x || !eps || !ms_out || iters < 1) {
+    set_error("drs_plan_time_forward: bad arguments");
+    return DRS_E_INVALID;
+  }
+  cudaEvent_t ev[3];
+  for (auto& e : ev) DRS_CUDA(cudaEventCreate(&e));
+  double acc0 = 0.0, acc1 = 0.0;
+  int rc = DRS_OK;
+  for (int it = 0; it < iters && rc == DRS_OK; ++it) {
+    rc = enqueue_forward(p, x, eps, st, ev);
+    if (rc != DRS_OK) break;
+    const cudaError_t se = cudaStreamSynchronize(st);
+    if (se != cudaSuccess) {
+      rc = cuda_fail(se, "cudaStreamSynchronize(time_forward)");
+      break;
+    }
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, ev[0], ev[1]);
+    cudaEventElapsedTime(&b, ev[1], ev[2]);
+    acc0 += a;
+    acc1 += b;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  ms_out[0] = static_cast<float>(acc0 / iters);
+  ms_out[1] = static_cast<float>(acc1 / iters);
+  return rc;
 }
 
 int check_pipeline_error(DrsPlan* p, cudaStream_t st) {

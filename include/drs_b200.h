@@ -115,6 +115,10 @@ int drs_plan_launch_count(const DrsPlan* p);
 int drs_plan_launch_info(const DrsPlan* p, int index, char* name, int name_capacity, double* flops, double* bytes,
                          int* ctas, int* smem_bytes);
 int drs_plan_profile(DrsPlan* p, const float* x_dev, float* eps_dev, int iters, float* ms_out, void* stream);
+/* Times the forward exactly as the sampler enqueues it (gate branch on the side stream, no event between the
+ * tensor-core launches): ms_out2[0] = conv0, ms_out2[1] = first tensor-core launch to completion of the last one,
+ * averaged over `iters` evaluations. Synchronises `stream`. */
+int drs_plan_time_forward(DrsPlan* p, const float* x_dev, float* eps_dev, int iters, float* ms_out2, void* stream);
 
 /* Stand-alone posterior update (train_diffusion_superres.py:240-249), scalars given directly. */
 int drs_ddpm_update(float* x_dev, const float* eps_dev, const float* noise_dev_or_null, float c1, float c2, float c3,

@@ -40,6 +40,9 @@ for i in range(nl):
     if name and name in nm.value.decode():
         print(f"launch {nm.value.decode()}: event time {float(ms[i]) * 1000:.1f} us; CTA 0 recorded span {last} cycles "
               f"= {last / 1.965e3:.1f} us at 1965 MHz")
+if buf[504]:
+    print("kernel stamps (cycles from entry): setup done %d, producer past griddep_wait %d, first pair start %d, exit %d" % (
+        buf[505] - buf[504], buf[506] - buf[504], buf[0] - buf[504], buf[507] - buf[504]))
 tr = [buf[256 + i] for i in range(64)]
 if any(tr):
     base = min(v for v in tr if v > 0)
