@@ -71,7 +71,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 template <int EPI>
 __device__ __forceinline__ void conv_epilogue(const EpiArgs& e, uint32_t taddr, int x, int y, int b, bool valid, int W,
                                               int H, int N, int oc_off, const float (*s_par)[kMaxN],
-                                              TmaStoreCtx* ts = nullptr) {
+                                              TmaStoreCtx* ts = nullptr, int g_begin = 0, int g_end = -1) {
+  if (g_end < 0) g_end = e.n_groups;
   if (EPI == EPI_STD) {
     const int flags = e.flags;
     const uint32_t lane = threadIdx.x & 31u;
@@ -95,7 +96,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiArgs& e, uint32_t taddr, 
     if ((flags & F_ROWSCALE) && valid)
       rs = __ldg(e.psi + (static_cast<size_t>(b) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1));
 
-    for (int g = 0; g < e.n_groups; ++g) {
+    for (int g = g_begin; g < g_end; ++g) {
       const int oy = (e.oscale == 2) ? (2 * y + (g >> 1)) : y;
       const int ox = (e.oscale == 2) ? (2 * x + (g & 1)) : x;
       __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(e.out) +
@@ -347,7 +348,7 @@ struct StdEpilogue {
 template <int FL>
 __device__ __forceinline__ void conv_epilogue_std_ct(const EpiArgs& e, uint32_t taddr, int x, int y, int b, bool valid,
                                                      int W, int H, int N, int oc_off, const float (*s_par)[kMaxN],
-                                                     const float* s_te, TmaStoreCtx* ts) {
+                                                     const float* s_te, TmaStoreCtx* ts, int g_begin, int g_end) {
   StdEpilogue<FL> E{e, s_par, s_te, nullptr, ts, nullptr, threadIdx.x & 31u, 0, 0, 0, 0, 1.0f, valid, oc_off};
   if (ts) {
     E.st_row = E.lane * static_cast<uint32_t>(ts->sbc) * 2u;
@@ -364,7 +365,6 @@ __device__ __forceinline__ void conv_epilogue_std_ct(const EpiArgs& e, uint32_t 
   if ((FL & F_ROWSCALE) && valid)
     E.rs = __ldg(e.psi + (static_cast<size_t>(b) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1));
 
-  const int n_groups = e.n_groups;
   if (StdEpilogue<FL>::kDual) {
     // two accumulators per chunk: single-buffered (32 registers), which keeps the kernel at two CTAs per SM
     uint32_t v[16], w[16];
@@ -378,13 +378,13 @@ __device__ __forceinline__ void conv_epilogue_std_ct(const EpiArgs& e, uint32_t 
     return;
   }
   uint32_t va[16], vb[16], wa[16], wb[16];
-  tmem_ld16_raw(taddr, va);
-  for (int g = 0; g < n_groups; ++g) {
+  tmem_ld16_raw(taddr + static_cast<uint32_t>(g_begin * N), va);
+  for (int g = g_begin; g < g_end; ++g) {
     const int oy = (e.oscale == 2) ? (2 * y + (g >> 1)) : y;
     const int ox = (e.oscale == 2) ? (2 * x + (g & 1)) : x;
     E.orow = reinterpret_cast<__nv_bfloat16*>(e.out) + ((static_cast<size_t>(b) * e.OH + oy) * e.OW + ox) * e.OC + oc_off;
     const uint32_t colbase = taddr + static_cast<uint32_t>(g * N);
-    const bool more_groups = (g + 1 < n_groups);
+    const bool more_groups = (g + 1 < g_end);
     for (int c0 = 0; c0 < N; c0 += 32) {
       // chunk A = [c0, c0 + 16): its load is in flight; start chunk B, work on A, then the same with roles swapped
       const bool has_b = (c0 + 16 < N);

@@ -112,7 +112,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&s_tfull[s], 1);
-      mbar_init(&s_tempty[s], 128);
+      mbar_init(&s_tempty[s], a.solo ? 256 : 128);
     }
     mbar_init(&s_wready, 1);
     fence_mbar_init();
@@ -286,7 +286,6 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     const int row = q * 32 + lane;
     const int lx = row & (kTile2W - 1);
     const int ly = row >> 3;
-    RingPos tr{0, 0};
     int pno = 0;
     TmaStoreCtx ts;
     ts.map = &map_out;
@@ -296,46 +295,59 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     // staging areas follow the weight region (both 1024-byte aligned)
     ts.stage = b_base + (a.resident ? a.w_split_bytes : static_cast<uint32_t>(a.b_stages * a.b_stage_bytes)) +
                static_cast<size_t>(warp) * kStageBytesPerWarp;
+    // Normal mode: group p drains pipeline p (all column groups). Solo mode (one accumulator buffer per pipeline and
+    // several column groups, i.e. the transposed convolutions): both groups drain EVERY tile, half of the column
+    // groups each, so the epilogue of tile k runs twice as fast and overlaps the MMAs of tile k + 1 of the other
+    // pipeline.
+    const int n_jobs = a.solo ? 2 : 1;
+    const int g_half = e.n_groups >> 1;
     for (int tile0 = first_tile; tile0 < a.n_tiles; tile0 += 2 * tile_step, ++pno) {
-      const int tile = tile0 + p * tile_step;
-      if (tile >= a.n_tiles) break;
-      const int tb = p * 2 + tr.idx;
-      const int b = tile / tiles_per_img;
-      const int t2 = tile - b * tiles_per_img;
-      const int y = (t2 / a.tiles_x) * kTile2H + ly;
-      const int x = (t2 % a.tiles_x) * kTile2W + lx;
-      const bool valid = (x < a.W) && (y < a.H);
-      if (kStageTe) {
-        // this tile's time-embedding row -> the warp's shared copy (latency hidden behind the accumulator wait)
-        __syncwarp();
-        const float* src = e.te + static_cast<size_t>(__ldg(e.trow + b)) * e.te_stride + e.te_off + oc_off;
-        for (int c = lane * 4; c < a.n_sub; c += 128)
-          *reinterpret_cast<float4*>(&s_te[warp][c]) = __ldg(reinterpret_cast<const float4*>(src + c));
-        __syncwarp();
-      }
-      mbar_wait(&s_tfull[tb], tr.phase, a.err, 3);
-      tc_fence_after();
-      if (threadIdx.x == 0) TL(pno, 5);
-      const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) +
-                             static_cast<uint32_t>((p * a.acc_bufs + tr.idx) * a.acc_cols);
-      ts.x0 = (t2 % a.tiles_x) * kTile2W;
-      ts.y0 = (t2 / a.tiles_x) * kTile2H + q * 4;
-      ts.b = b;
+      for (int job = 0; job < n_jobs; ++job) {
+        const int pp = a.solo ? job : p;  // pipeline whose tile is drained
+        const int tile = tile0 + pp * tile_step;
+        if (tile >= a.n_tiles) continue;
+        // pipeline pp uses buffer (pno mod acc_bufs) for its pno-th tile
+        const int bi = (a.acc_bufs == 2) ? (pno & 1) : 0;
+        const uint32_t ph = static_cast<uint32_t>((a.acc_bufs == 2) ? (pno >> 1) : pno) & 1u;
+        const int tb = pp * 2 + bi;
+        const int g_begin = a.solo ? p * g_half : 0;
+        const int g_end = a.solo ? g_begin + g_half : e.n_groups;
+        const int b = tile / tiles_per_img;
+        const int t2 = tile - b * tiles_per_img;
+        const int y = (t2 / a.tiles_x) * kTile2H + ly;
+        const int x = (t2 % a.tiles_x) * kTile2W + lx;
+        const bool valid = (x < a.W) && (y < a.H);
+        if (kStageTe) {
+          // this tile's time-embedding row -> the warp's shared copy (latency hidden behind the accumulator wait)
+          __syncwarp();
+          const float* src = e.te + static_cast<size_t>(__ldg(e.trow + b)) * e.te_stride + e.te_off + oc_off;
+          for (int c = lane * 4; c < a.n_sub; c += 128)
+            *reinterpret_cast<float4*>(&s_te[warp][c]) = __ldg(reinterpret_cast<const float4*>(src + c));
+          __syncwarp();
+        }
+        mbar_wait(&s_tfull[tb], ph, a.err, 3);
+        tc_fence_after();
+        if (threadIdx.x == 0) TL(pno, 5);
+        const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>((pp * a.acc_bufs + bi) * a.acc_cols);
+        ts.x0 = (t2 % a.tiles_x) * kTile2W;
+        ts.y0 = (t2 / a.tiles_x) * kTile2H + q * 4;
+        ts.b = b;
 #ifdef DRS_EPI_TRACE
-      if (threadIdx.x == 0 && blockIdx.x == 0) g_epi_trace_on = ((a.timeline & 1) && pno == 3) ? 1 : 0;
+        if (threadIdx.x == 0 && blockIdx.x == 0) g_epi_trace_on = ((a.timeline & 1) && pno == 3) ? 1 : 0;
 #endif
-      if (!(a.timeline & 2)) {
-        if constexpr (EPI == EPI_STD && FL >= 0)
-          conv_epilogue_std_ct<FL>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par, s_te[kStageTe ? warp : 0],
-                                   a.store_sbc ? &ts : nullptr);
-        else
-          conv_epilogue<EPI>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par,
-                             (EPI == EPI_STD && a.store_sbc) ? &ts : nullptr);
+        if (!(a.timeline & 2)) {
+          if constexpr (EPI == EPI_STD && FL >= 0)
+            conv_epilogue_std_ct<FL>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par,
+                                     s_te[kStageTe ? warp : 0], a.store_sbc ? &ts : nullptr, g_begin, g_end);
+          else
+            conv_epilogue<EPI>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par,
+                               (EPI == EPI_STD && a.store_sbc) ? &ts : nullptr, g_begin, g_end);
+        }
+        tc_fence_before();
+        mbar_arrive(&s_tempty[tb]);
+        if (threadIdx.x == 0) TL(pno, 6);
       }
-      tc_fence_before();
-      mbar_arrive(&s_tempty[tb]);
-      if (threadIdx.x == 0) TL(pno, 6);
-      tr.advance(a.acc_bufs);
     }
     // the staging areas must outlive the TMA unit's reads
     if (EPI == EPI_STD && a.store_sbc && lane == 0) bulk_wait_read<0>();

@@ -86,6 +86,7 @@ struct Conv2Args {
   int acc_cols;             // columns one tile's accumulators use
   int acc_bufs;             // 1 or 2
   int n_sub, nsplit;
+  int solo;                 // 1: both epilogue groups drain every tile, half of the column groups each
   int store_sbc;            // EPI_STD: channels per TMA-store sub-box (0: per-thread global stores, no staging)
   int timeline;             // debug: CTA 0 records clock stamps (DRS_V2_TIMELINE)
   int* err;

@@ -311,7 +311,8 @@ struct Builder {
     // Streamed weights travel in units of up to b_unit consecutive K-blocks of one sub-tile (<= 32 KiB): one bulk
     // copy, one full / empty barrier round trip and one tcgen05.commit per unit instead of per K-block.
     const int tile_pad = (max_b + 1023) & ~1023;
-    v.b_unit = std::max(1, std::min(4, (32 * 1024) / tile_pad));
+    static const int unit_kib = getenv("DRS_V2_BUNIT_KIB") ? atoi(getenv("DRS_V2_BUNIT_KIB")) : 32;
+    v.b_unit = std::max(1, std::min(4, (unit_kib * 1024) / tile_pad));
     v.b_stage_bytes = v.resident ? tile_pad : v.b_unit * tile_pad;
     v.w_split_bytes = static_cast<uint32_t>(w_image);
     while (m->wblob.size() % 1024) m->wblob.push_back(0);

@@ -223,6 +223,10 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   a.tmem_cols = alloc;
   a.n_sub = g.n_sub;
   a.nsplit = g.nsplit;
+  // transposed convolutions (four column groups, one accumulator buffer per pipeline): both epilogue groups work on
+  // every tile
+  static const bool no_solo = (getenv("DRS_V2_NO_SOLO") != nullptr);
+  a.solo = (!no_solo && g.epi_kind == EPI_STD && a.acc_bufs == 1 && g.n_groups >= 2 && g.n_groups % 2 == 0) ? 1 : 0;
   a.err = p->d_err;
   static const int timeline = getenv("DRS_V2_TIMELINE") ? atoi(getenv("DRS_V2_TIMELINE")) : 0;
   // bit 0: record stamps, bit 1: skip the epilogue body (timing experiments only); DRS_V2_TIMELINE_LAYER restricts
