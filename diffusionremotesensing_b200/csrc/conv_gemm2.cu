@@ -26,6 +26,11 @@ namespace drs {
 // 0 producer pair start, 1 producer last issue, 2 MMA(0) after tmem-empty wait, 3 MMA(0) after first A-full wait,
 // 4 MMA(0) after last issue, 5 epilogue(0) after tmem-full wait, 6 epilogue(0) done, 7 MMA(1) after last issue.
 __device__ long long g_timeline[64 * 8];
+long long* conv_gemm2_timeline_dev() {
+  long long* p = nullptr;
+  cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_timeline);
+  return p;
+}
 #define TL(tile_no, slot)                                                                       \
   do {                                                                                          \
     if ((a.timeline & 1) && blockIdx.x == 0 && (tile_no) < 64) g_timeline[(tile_no) * 8 + (slot)] = clock64(); \

@@ -86,8 +86,10 @@ struct Conv2Args {
   int acc_cols;             // columns one tile's accumulators use
   int acc_bufs;             // 1 or 2
   int n_sub, nsplit;
+  int cg2_half_tile_bytes;  // CTA-pair kernel: bytes of half a (padded) weight tile
   int solo;                 // 1: both epilogue groups drain every tile, half of the column groups each
   int store_sbc;            // EPI_STD: channels per TMA-store sub-box (0: per-thread global stores, no staging)
+  long long* timeline_buf;  // debug: device buffer of the stamps (CTA-pair kernel)
   int timeline;             // debug: CTA 0 records clock stamps (DRS_V2_TIMELINE)
   int* err;
   EpiArgs epi;
@@ -100,6 +102,14 @@ int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& 
                       const Conv2Args& args,
                       const Conv2Prog& prog, int grid, size_t smem_bytes, cudaStream_t stream);
 int conv_gemm2_set_smem_limits();
+// CTA-pair variant (conv_gemm2c.cu)
+int launch_conv_gemm2c(const CUtensorMap& map0, const CUtensorMap& map1, const CUtensorMap& map_out,
+                       const CUtensorMap& map_w, const Conv2Args& args, const Conv2Prog& prog, int grid,
+                       size_t smem_bytes, cudaStream_t stream);
+int conv_gemm2c_set_smem_limits();
+bool conv_gemm2c_supports(int epi_kind, int flags);
+int conv_gemm2c_max_clusters(int flags, size_t smem_bytes);
 int conv_gemm2_read_timeline(long long* host, int n);
+long long* conv_gemm2_timeline_dev();  // device address of the debug timeline buffer (shared with conv_gemm2c.cu)
 
 }  // namespace drs

@@ -158,6 +158,13 @@ struct Launch {
   Conv2Args args2;
   const Conv2Prog* prog2 = nullptr;  // points into the model's GemmSpec
   int grid2 = 0;
+  // CTA-pair kernel (conv_gemm2c.cu): its own argument block, weight-offset program, weight tensor map, grid, smem
+  bool use_cg2 = false;
+  Conv2Args args_c;
+  Conv2Prog prog_c;
+  CUtensorMap map_w;
+  int grid_c = 0;
+  size_t smem_c = 0;
 };
 
 }  // namespace drs

@@ -819,6 +819,7 @@ int model_create(const DrsModelDesc* desc, const DrsTensor* tensors, int n_tenso
   DRS_TRY(m->d_kblocks.upload(m->kb_all.data(), m->kb_all.size() * sizeof(KBlock)));
   int r = conv_gemm_set_smem_limits();
   if (r == 0) r = conv_gemm2_set_smem_limits();
+  if (r == 0) r = conv_gemm2c_set_smem_limits();
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "cudaFuncSetAttribute(conv_gemm_kernel)");
   // the host copy of the state_dict is no longer needed
   m->sd.clear();
@@ -863,6 +864,7 @@ int build_debug_conv(DrsModel* m, const float* w, const float* bias, const float
   DRS_TRY(m->d_kblocks.upload(m->kb_all.data(), m->kb_all.size() * sizeof(KBlock)));
   int r = conv_gemm_set_smem_limits();
   if (r == 0) r = conv_gemm2_set_smem_limits();
+  if (r == 0) r = conv_gemm2c_set_smem_limits();
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "cudaFuncSetAttribute(conv_gemm_kernel)");
   return DRS_OK;
 }

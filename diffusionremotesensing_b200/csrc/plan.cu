@@ -269,7 +269,11 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   a.a_slots = slots;
   a.store_sbc = 0;
   if (stage_bytes) {
-    a.store_sbc = std::min(64, g.n_sub);
+    // One sub-box per tile (N <= 64, one column group) can use the whole 4 KiB staging area; with several sub-boxes
+    // per tile a single buffer would make every sub-box wait for the TMA unit to read the previous one, so the area
+    // is split into two 32-channel (or four 16-channel) buffers that rotate.
+    static const int sbc_multi = getenv("DRS_V2_SBC_MULTI") ? atoi(getenv("DRS_V2_SBC_MULTI")) : 64;
+    a.store_sbc = (g.n_sub * g.n_groups > 64) ? std::min(sbc_multi, g.n_sub) : std::min(64, g.n_sub);
     const int r = make_map(&L->map_out, a.epi.out, p->nb, a.epi.OH, a.epi.OW, a.epi.OC, g.oscale == 2, a.store_sbc,
                            kTile2W, 4, 1, 1);
     if (r != DRS_OK) return r;
@@ -286,8 +290,114 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   return DRS_OK;
 }
 
+// CTA-pair binding (conv_gemm2c.cu) on top of a successful second-generation binding. Taken for the launches named in
+// DRS_CG2 (comma separated fragments, "all", or "streamed" = every launch whose weights are not resident otherwise).
+static bool cg2_wanted(const std::string& name, bool resident_v2, bool resident_cg2) {
+  // Default: take the CTA pair where it turns streamed weights into resident ones (measured: up_convs.1 73 -> 56 us at
+  // cfg 2; streamed-in-both-modes layers do not gain). DRS_CG2 = none | all | streamed | <name fragments> overrides.
+  static const char* const env = getenv("DRS_CG2");
+  if (!env) return !resident_v2 && resident_cg2;
+  const std::string list = env;
+  if (list == "none") return false;
+  if (list == "all") return true;
+  size_t pos = 0;
+  while (pos <= list.size()) {
+    const size_t e = list.find(',', pos);
+    const std::string frag = list.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+    if (frag == "streamed" && !resident_v2) return true;
+    if (!frag.empty() && frag != "streamed" && name.find(frag) != std::string::npos) return true;
+    if (e == std::string::npos) break;
+    pos = e + 1;
+  }
+  return false;
+}
+
+static int bind_launch_cg2(DrsPlan* p, Launch* L) {
+  const DrsModel* m = p->m;
+  const GemmSpec& g = m->gemms[L->spec];
+  const GemmSpec::V2& v = g.v2;
+  L->use_cg2 = false;
+  if (!L->use_v2 || !conv_gemm2c_supports(g.epi_kind, g.flags)) return DRS_OK;
+  const Conv2Args& a2 = L->args2;
+  if (a2.n_tiles % 2) return DRS_OK;
+  // one weight-tile size per launch, half of it a whole number of 1 KiB swizzle atoms
+  const uint32_t tile_bytes = v.prog.kb[0].b_bytes & 0xFFFFFFu;
+  if (tile_bytes % 2048) return DRS_OK;
+  for (int i = 0; i < v.nkb; ++i)
+    if ((v.prog.kb[i].b_bytes & 0xFFFFFFu) != tile_bytes) return DRS_OK;
+  if (static_cast<uint64_t>(tile_bytes) * v.nkb != v.w_split_bytes) return DRS_OK;
+  const int half = static_cast<int>(tile_bytes / 2);
+  if ((half >> 7) > 256) return DRS_OK;  // TMA box rows
+
+  Conv2Args a = a2;
+  a.cg2_half_tile_bytes = half;
+  a.timeline_buf = a.timeline ? conv_gemm2_timeline_dev() : nullptr;
+  const int half_image = static_cast<int>(v.w_split_bytes / 2);
+  const int budget = 227 * 1024 - 14 * 1024;
+  const int spt = a.n_sub_tiles;
+  const int want_slots = std::min(kMaxASlots, std::max(4, 2 * spt + 2));
+  // resident when this CTA's half image leaves room for four A slots
+  a.resident = (half_image + 4 * v.a_slot_bytes <= budget) ? 1 : 0;
+  if (!cg2_wanted(g.name, v.resident, a.resident != 0)) return DRS_OK;
+  a.b_unit = v.b_unit;
+  a.b_stage_bytes = v.b_unit * half;
+  a.b_stages = a.resident ? 1 : std::min(std::min(4, kMaxBStages), (v.nkb + v.b_unit - 1) / v.b_unit);
+  const int b_bytes = a.resident ? half_image : a.b_stages * a.b_stage_bytes;
+  int stage_bytes = a.store_sbc ? kStageBytes : 0;
+  if (stage_bytes && (((budget - b_bytes - stage_bytes) / v.a_slot_bytes) & ~1) < 4) {
+    stage_bytes = 0;
+    a.store_sbc = 0;
+  }
+  const int slots = std::min(want_slots, (budget - b_bytes - stage_bytes) / v.a_slot_bytes) & ~1;
+  if (slots < 2) return DRS_OK;
+  a.a_slots = slots;
+  L->smem_c = static_cast<size_t>(slots) * v.a_slot_bytes + b_bytes + stage_bytes + 1024;
+
+  // weight offsets: absolute inside the (half) image when resident, else relative to the K-block's ring unit
+  L->prog_c = v.prog;
+  for (int i = 0; i < v.nkb;) {
+    const int cnt = static_cast<int>(v.prog.kb[i].b_bytes >> 24);
+    for (int j = 0; j < cnt; ++j) {
+      const int first = i + (j / v.b_unit) * v.b_unit;
+      const uint32_t off = a.resident ? v.prog.kb[i + j].b_off : (v.prog.kb[i + j].b_off - v.prog.kb[first].b_off);
+      L->prog_c.kb[i + j].b_lo = (off / 16) | 0x10000u;
+    }
+    i += cnt;
+  }
+  // the packed weight blob as rows of 128 bytes; one box = this CTA's half of one tile
+  {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return DRS_OK;
+    const cuuint64_t rows = m->d_wblob.bytes / 128;
+    const cuuint64_t dims[2] = {64, rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(half >> 7)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(&L->map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(m->d_wblob.p), dims, strides,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return DRS_OK;
+  }
+  const int max_clusters = conv_gemm2c_max_clusters(g.flags, L->smem_c);
+  if (max_clusters < g.nsplit) return DRS_OK;
+  const int n_units = a.n_tiles / 2;
+  int clusters = std::min(((n_units + 1) / 2) * g.nsplit, max_clusters);
+  clusters -= clusters % g.nsplit;
+  if (clusters < g.nsplit) return DRS_OK;
+  L->grid_c = 2 * clusters;
+  L->args_c = a;
+  L->use_cg2 = true;
+  static const bool verbose = (getenv("DRS_V2_VERBOSE") != nullptr);
+  if (verbose)
+    fprintf(stderr, "[drs] %s: CTA-pair kernel, %d clusters, %s weights (%d KiB per CTA), %d A slots, smem %zu\n",
+            g.name.c_str(), clusters, a.resident ? "resident" : "streamed", b_bytes / 1024, slots, L->smem_c);
+  return DRS_OK;
+}
+
 static int launch_one(const DrsPlan* p, const Launch& L, float* eps, cudaStream_t st) {
   const GemmSpec& g = p->m->gemms[L.spec];
+  if (L.use_cg2)
+    return launch_conv_gemm2c(L.map0, L.map1, L.map_out, L.map_w, L.args_c, L.prog_c, L.grid_c, L.smem_c, st);
   if (L.use_v2) {
     Conv2Args a = L.args2;
     if (g.epi_kind == EPI_OUT && eps) a.epi.out = eps;
@@ -414,6 +524,7 @@ int plan_create(DrsModel* m, int nb, int nx, int ncond, int S, int mag, DrsPlan*
     DRS_TRY(bind_launch(p.get(), static_cast<int>(gi), src[0], src[1], gridW, gridH, sH, sW, outp, OH, OW, &L));
     if (g.flags & F_ROWSCALE) L.args.epi.psi = reinterpret_cast<const float*>(ws + p->acts.at(g.src_name[1]).offset);
     DRS_TRY(bind_launch_v2(p.get(), src[0], src[1], gridW, gridH, sH, sW, &L));
+    DRS_TRY(bind_launch_cg2(p.get(), &L));
     p->launches.push_back(L);
   }
   *out = p.release();
@@ -833,6 +944,7 @@ int debug_bind_and_run(DrsPlan* p, const void* in, int gridW, int gridH, int src
   Launch L;
   DRS_TRY(bind_launch(p, 0, in, nullptr, gridW, gridH, sH, sW, out, OH, OW, &L));
   DRS_TRY(bind_launch_v2(p, in, nullptr, gridW, gridH, sH, sW, &L));
+  DRS_TRY(bind_launch_cg2(p, &L));
   const int r = launch_one(p, L, nullptr, st);
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "launch_conv_gemm(debug)");
   return DRS_OK;
@@ -892,8 +1004,8 @@ int launch_info(const DrsPlan* p, int i, char* name, int name_cap, double* flops
       b += grid_px * g.oscale * g.oscale * g.OC * 2;
     *bytes = b;
   }
-  if (ctas) *ctas = L.use_v2 ? -L.grid2 : L.n_tiles * g.nsplit;  // negative: persistent second-generation grid
-  if (smem_bytes) *smem_bytes = static_cast<int>(L.smem);
+  if (ctas) *ctas = L.use_cg2 ? -L.grid_c : (L.use_v2 ? -L.grid2 : L.n_tiles * g.nsplit);  // negative: persistent grid
+  if (smem_bytes) *smem_bytes = static_cast<int>(L.use_cg2 ? L.smem_c : L.smem);
   return DRS_OK;
 }
 
