@@ -1,0 +1,47 @@
+"""The alternative code paths of the convolution kernel, each forced through its environment switch in a child
+process (the switches are read once per process) and checked with the same layer-level parity cases as the default
+path (tests/test_gpu_conv_layers.py):
+
+  * DRS_CG2=all             CTA-pair kernel (tcgen05.mma.cta_group::2, conv_gemm2c.cu) wherever it is applicable
+  * DRS_V2_NO_TMA_STORE=1   per-thread global stores instead of the staged TMA-store epilogue
+  * DRS_V2_GENERIC_EPILOGUE run-time flag epilogue instead of the compile-time variants
+  * DRS_V2_NO_SOLO=1        transposed convolutions drained by one epilogue group per tile
+  * DRS_DISABLE_V2=1        first-generation kernel for every layer
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_child(extra_env, args):
+    env = dict(os.environ)
+    env.update(extra_env)
+    env["DRS_V2_VERBOSE"] = "1"
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-s", "-m", "gpu", "-p", "no:cacheprovider"] + args
+    return subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+
+
+@pytest.mark.parametrize("env", [{"DRS_V2_NO_TMA_STORE": "1"}, {"DRS_V2_GENERIC_EPILOGUE": "1"}, {"DRS_V2_NO_SOLO": "1"},
+                                 {"DRS_DISABLE_V2": "1"}, {"DRS_V2_NO_PDL": "1"}])
+def test_layer_parity_on_alternative_paths(cuda_device, env):
+    r = run_child(env, ["tests/test_gpu_conv_layers.py"])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_cta_pair_kernel_layer_parity(cuda_device):
+    r = run_child({"DRS_CG2": "all"}, ["tests/test_gpu_conv_layers.py"])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    # the switch must really have routed launches through the CTA-pair kernel
+    assert "CTA-pair kernel" in r.stderr or "CTA-pair kernel" in r.stdout, "no launch used the CTA-pair kernel"
+
+
+def test_cta_pair_kernel_unet_parity(cuda_device):
+    r = run_child({"DRS_CG2": "all"}, ["tests/test_gpu_unet.py"])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "CTA-pair kernel" in r.stderr or "CTA-pair kernel" in r.stdout
