@@ -363,6 +363,10 @@ conv_gemm2c_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     tc_fence_after();
     tmem_dealloc_2cta(tmem, static_cast<uint32_t>(a.tmem_cols));
   }
+  // The pair-wide deallocation is a collective of one warp of each CTA. Neither CTA may retire before both have
+  // executed it: the next kernel's CTA on that SM could otherwise enter the collective in its place (observed as an
+  // illegal-address fault whenever one CTA-pair launch directly followed another).
+  cluster_sync_all();
 }
 
 #define DRS_GEMM2C_VARIANTS(X) \
@@ -424,8 +428,7 @@ int conv_gemm2c_max_clusters(int flags, size_t smem_bytes) {
 int launch_conv_gemm2c(const CUtensorMap& map0, const CUtensorMap& map1, const CUtensorMap& map_out,
                        const CUtensorMap& map_w, const Conv2Args& args, const Conv2Prog& prog, int grid,
                        size_t smem_bytes, cudaStream_t stream) {
-  // DRS_CG2_PDL=1: also launch the cluster kernel itself as a programmatic dependent (experiment)
-  static const bool no_pdl = (getenv("DRS_V2_NO_PDL") != nullptr) || (getenv("DRS_CG2_PDL") == nullptr);
+  static const bool no_pdl = (getenv("DRS_V2_NO_PDL") != nullptr);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);

@@ -378,6 +378,10 @@ static int bind_launch_cg2(DrsPlan* p, Launch* L) {
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return DRS_OK;
   }
+  // one CTA pair per TPC: pad the request so that no second CTA fits beside it (two co-resident pairs interleave
+  // their TMEM pair allocations)
+  static const int min_smem = getenv("DRS_CG2_MIN_SMEM_KIB") ? atoi(getenv("DRS_CG2_MIN_SMEM_KIB")) * 1024 : 116 * 1024;
+  if (L->smem_c < static_cast<size_t>(min_smem)) L->smem_c = static_cast<size_t>(min_smem);
   const int max_clusters = conv_gemm2c_max_clusters(g.flags, L->smem_c);
   if (max_clusters < g.nsplit) return DRS_OK;
   const int n_units = a.n_tiles / 2;
@@ -646,6 +650,7 @@ static void rebind_table(DrsPlan* p) {
   for (Launch& L : p->launches) {
     L.args.epi.te = p->table.as<float>();
     L.args2.epi.te = p->table.as<float>();
+    L.args_c.epi.te = p->table.as<float>();
   }
 }
 

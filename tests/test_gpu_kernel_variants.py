@@ -41,7 +41,9 @@ def test_cta_pair_kernel_layer_parity(cuda_device):
     assert "CTA-pair kernel" in r.stderr or "CTA-pair kernel" in r.stdout, "no launch used the CTA-pair kernel"
 
 
-def test_cta_pair_kernel_unet_parity(cuda_device):
-    r = run_child({"DRS_CG2": "all"}, ["tests/test_gpu_unet.py"])
+def test_cta_pair_kernel_unet_and_sampler_parity(cuda_device):
+    # the sampler tests re-allocate the time table after the plan was bound: every launch argument block, the
+    # CTA-pair one included, has to follow (regression test for a stale pointer)
+    r = run_child({"DRS_CG2": "all"}, ["tests/test_gpu_unet.py", "tests/test_gpu_sampler.py"])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "CTA-pair kernel" in r.stderr or "CTA-pair kernel" in r.stdout
