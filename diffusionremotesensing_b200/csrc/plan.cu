@@ -292,11 +292,13 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
 
 // CTA-pair binding (conv_gemm2c.cu) on top of a successful second-generation binding. Taken for the launches named in
 // DRS_CG2 (comma separated fragments, "all", or "streamed" = every launch whose weights are not resident otherwise).
-static bool cg2_wanted(const std::string& name, bool resident_v2, bool resident_cg2) {
-  // Default: take the CTA pair where it turns streamed weights into resident ones (measured: up_convs.1 73 -> 56 us at
-  // cfg 2; streamed-in-both-modes layers do not gain). DRS_CG2 = none | all | streamed | <name fragments> overrides.
+static bool cg2_wanted(const std::string& name, bool resident_v2, bool resident_cg2, int nkb) {
+  // Default (measured at cfg 2, profiles/layers_r1f.json): take the CTA pair where it turns streamed weights into
+  // resident ones (up_convs.1: 73 -> 56 us) and for the long streamed K loops, whose half-size weight tiles let one
+  // ring stage carry four K-blocks (up_convs.0: 58 -> 52 us; 36 K-blocks: break-even; shorter loops lose a few
+  // percent to the cluster hand-shakes). DRS_CG2 = none | all | streamed | <name fragments> overrides.
   static const char* const env = getenv("DRS_CG2");
-  if (!env) return !resident_v2 && resident_cg2;
+  if (!env) return !resident_v2 && (resident_cg2 || nkb >= 36);
   const std::string list = env;
   if (list == "none") return false;
   if (list == "all") return true;
@@ -338,10 +340,14 @@ static int bind_launch_cg2(DrsPlan* p, Launch* L) {
   const int want_slots = std::min(kMaxASlots, std::max(4, 2 * spt + 2));
   // resident when this CTA's half image leaves room for four A slots
   a.resident = (half_image + 4 * v.a_slot_bytes <= budget) ? 1 : 0;
-  if (!cg2_wanted(g.name, v.resident, a.resident != 0)) return DRS_OK;
-  a.b_unit = v.b_unit;
-  a.b_stage_bytes = v.b_unit * half;
-  a.b_stages = a.resident ? 1 : std::min(std::min(4, kMaxBStages), (v.nkb + v.b_unit - 1) / v.b_unit);
+  if (!cg2_wanted(g.name, v.resident, a.resident != 0, v.nkb)) return DRS_OK;
+  // half-size tiles: twice as many K-blocks per ring stage for the same bytes (fewer full / empty round trips)
+  static const int cg2_unit_kib = getenv("DRS_CG2_BUNIT_KIB") ? atoi(getenv("DRS_CG2_BUNIT_KIB")) : 32;
+  const int unit_c = std::max(1, std::min(8, (cg2_unit_kib * 1024) / half));
+  a.b_unit = unit_c;
+  a.b_stage_bytes = unit_c * half;
+  static const int cg2_stages = getenv("DRS_CG2_BSTAGES") ? atoi(getenv("DRS_CG2_BSTAGES")) : 3;
+  a.b_stages = a.resident ? 1 : std::min(std::min(cg2_stages, kMaxBStages), (v.nkb + unit_c - 1) / unit_c);
   const int b_bytes = a.resident ? half_image : a.b_stages * a.b_stage_bytes;
   int stage_bytes = a.store_sbc ? kStageBytes : 0;
   if (stage_bytes && (((budget - b_bytes - stage_bytes) / v.a_slot_bytes) & ~1) < 4) {
@@ -358,7 +364,7 @@ static int bind_launch_cg2(DrsPlan* p, Launch* L) {
   for (int i = 0; i < v.nkb;) {
     const int cnt = static_cast<int>(v.prog.kb[i].b_bytes >> 24);
     for (int j = 0; j < cnt; ++j) {
-      const int first = i + (j / v.b_unit) * v.b_unit;
+      const int first = i + (j / unit_c) * unit_c;
       const uint32_t off = a.resident ? v.prog.kb[i + j].b_off : (v.prog.kb[i + j].b_off - v.prog.kb[first].b_off);
       L->prog_c.kb[i + j].b_lo = (off / 16) | 0x10000u;
     }
