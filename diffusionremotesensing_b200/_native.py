@@ -70,6 +70,7 @@ SIGNATURES = {
     "drs_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "drs_debug_mma_rate2": (C.c_int, [C.c_int] * 7 + [C.c_void_p]),
     "drs_debug_timeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "drs_debug_spans": (C.c_int, [C.c_void_p, C.c_int]),
     "drs_debug_fetch": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 

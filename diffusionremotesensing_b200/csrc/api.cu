@@ -291,6 +291,12 @@ int drs_debug_mma_rate2(int n, int nk, int layout, int sbo16, int issuers, int i
   return DRS_OK;
 }
 
+int drs_debug_spans(unsigned long long* out_host, int reset) {
+  const int r = conv_gemm2_spans(out_host, reset);
+  if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "conv_gemm2_spans");
+  return DRS_OK;
+}
+
 int drs_debug_timeline(long long* out_host, int n) {
   const int r = conv_gemm2_read_timeline(out_host, n);
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "cudaMemcpyFromSymbol(g_timeline)");

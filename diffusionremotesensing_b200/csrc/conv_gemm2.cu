@@ -26,6 +26,13 @@ namespace drs {
 // 0 producer pair start, 1 producer last issue, 2 MMA(0) after tmem-empty wait, 3 MMA(0) after first A-full wait,
 // 4 MMA(0) after last issue, 5 epilogue(0) after tmem-full wait, 6 epilogue(0) done, 7 MMA(1) after last issue.
 __device__ long long g_timeline[64 * 8];
+// DRS_V2_TIMELINE bit 2: per-launch [first CTA entry, last CTA exit] in globaltimer nanoseconds, by launch id
+__device__ unsigned long long g_span[64][2];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 long long* conv_gemm2_timeline_dev() {
   long long* p = nullptr;
   cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_timeline);
@@ -76,6 +83,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
                   const __grid_constant__ Conv2Prog prog) {
   extern __shared__ uint8_t dyn_smem[];
   if ((a.timeline & 1) && blockIdx.x == 0 && threadIdx.x == 0) g_timeline[504] = clock64();
+  if ((a.timeline & 4) && threadIdx.x == 0) atomicMin(&g_span[a.launch_id & 63][0], globaltimer_ns());
   __shared__ __align__(8) uint64_t s_afull[kMaxASlots], s_aempty[kMaxASlots];
   __shared__ __align__(8) uint64_t s_bfull[kMaxBStages], s_bempty[kMaxBStages];
   __shared__ __align__(8) uint64_t s_tfull[4], s_tempty[4];  // [tile of pair][accumulator buffer]
@@ -365,6 +373,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem, static_cast<uint32_t>(a.tmem_cols));
     if ((a.timeline & 1) && blockIdx.x == 0 && lane == 0) g_timeline[507] = clock64();
+    if ((a.timeline & 4) && lane == 0) atomicMax(&g_span[a.launch_id & 63][1], globaltimer_ns());
   }
 }
 
@@ -391,6 +400,24 @@ int conv_gemm2_set_smem_limits() {
   DRS_GEMM2_VARIANTS(X)
 #undef X
   return static_cast<int>(e);
+}
+
+unsigned long long* conv_gemm2_span_dev() {
+  unsigned long long* p = nullptr;
+  cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_span);
+  return p;
+}
+
+int conv_gemm2_spans(unsigned long long* host, int reset) {
+  if (reset) {
+    unsigned long long init[64][2];
+    for (auto& r : init) {
+      r[0] = ~0ull;
+      r[1] = 0ull;
+    }
+    return static_cast<int>(cudaMemcpyToSymbol(g_span, init, sizeof(init)));
+  }
+  return static_cast<int>(cudaMemcpyFromSymbol(host, g_span, sizeof(unsigned long long) * 128));
 }
 
 int conv_gemm2_read_timeline(long long* host, int n) {

@@ -89,7 +89,9 @@ struct Conv2Args {
   int cg2_half_tile_bytes;  // CTA-pair kernel: bytes of half a (padded) weight tile
   int solo;                 // 1: both epilogue groups drain every tile, half of the column groups each
   int store_sbc;            // EPI_STD: channels per TMA-store sub-box (0: per-thread global stores, no staging)
+  unsigned long long* span_buf;  // debug: device address of the span table (CTA-pair kernel)
   long long* timeline_buf;  // debug: device buffer of the stamps (CTA-pair kernel)
+  int launch_id;            // index of the launch inside the plan (debug spans)
   int timeline;             // debug: CTA 0 records clock stamps (DRS_V2_TIMELINE)
   int* err;
   EpiArgs epi;
@@ -110,6 +112,8 @@ int conv_gemm2c_set_smem_limits();
 bool conv_gemm2c_supports(int epi_kind, int flags);
 int conv_gemm2c_max_clusters(int flags, size_t smem_bytes);
 int conv_gemm2_read_timeline(long long* host, int n);
+int conv_gemm2_spans(unsigned long long* host, int reset);  // debug: [launch id][entry, exit] globaltimer ns
+unsigned long long* conv_gemm2_span_dev();
 long long* conv_gemm2_timeline_dev();  // device address of the debug timeline buffer (shared with conv_gemm2c.cu)
 
 }  // namespace drs

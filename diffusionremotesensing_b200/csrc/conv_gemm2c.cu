@@ -83,6 +83,11 @@ conv_gemm2c_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
   constexpr bool kStageTe = (FL & F_TE) != 0;
   __shared__ __align__(16) float s_te[kStageTe ? 8 : 1][kStageTe ? kMaxN : 4];
 
+  if ((a.timeline & 4) && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin(&a.span_buf[(a.launch_id & 63) * 2], t);
+  }
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -367,6 +372,11 @@ conv_gemm2c_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
   // executed it: the next kernel's CTA on that SM could otherwise enter the collective in its place (observed as an
   // illegal-address fault whenever one CTA-pair launch directly followed another).
   cluster_sync_all();
+  if ((a.timeline & 4) && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(&a.span_buf[(a.launch_id & 63) * 2 + 1], t);
+  }
 }
 
 #define DRS_GEMM2C_VARIANTS(X) \

@@ -233,6 +233,7 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   // the recording to launches whose name contains the given substring
   static const char* const tl_layer = getenv("DRS_V2_TIMELINE_LAYER");
   a.timeline = (!tl_layer || g.name.find(tl_layer) != std::string::npos) ? timeline : 0;
+  a.launch_id = static_cast<int>(p->launches.size());  // bound just before being appended
   a.epi = L->args.epi;
   // shared memory: weights (resident image or a ring) + A slots. A pair of tiles consumes slots in the order
   // (sub-tile, tile-of-pair) and every slot is released after its own taps, so two slots per sub-tile in flight plus
@@ -334,6 +335,7 @@ static int bind_launch_cg2(DrsPlan* p, Launch* L) {
   Conv2Args a = a2;
   a.cg2_half_tile_bytes = half;
   a.timeline_buf = a.timeline ? conv_gemm2_timeline_dev() : nullptr;
+  a.span_buf = a.timeline ? conv_gemm2_span_dev() : nullptr;
   const int half_image = static_cast<int>(v.w_split_bytes / 2);
   const int budget = 227 * 1024 - 14 * 1024;
   const int spt = a.n_sub_tiles;

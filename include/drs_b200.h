@@ -149,6 +149,9 @@ int drs_debug_conv2d(const float* x_dev, const float* w_host, const float* bias_
  * variable DRS_V2_TIMELINE is set (8 values per pixel tile: producer start / last issue, MMA after TMEM-empty wait /
  * after first A-full wait / after last issue, epilogue after TMEM-full wait / done). n <= 512. */
 int drs_debug_timeline(long long* out_host, int n);
+/* Debug: with DRS_V2_TIMELINE bit 2 set every second-generation launch records [first CTA entry, last CTA exit] in
+ * globaltimer nanoseconds under its launch index. reset != 0 re-arms the table, else it is copied to out_host[128]. */
+int drs_debug_spans(unsigned long long* out_host, int reset);
 
 /* Debug micro-benchmark: one elected thread per CTA issues `iters` (x4 if unroll4) back-to-back tcgen05.mma
  * M=128 x n x K=16 (bf16) on shared-memory operands, `ctas_per_sm` CTAs per SM. out_host[0] = SM cycles until the
