@@ -374,6 +374,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     tmem_dealloc(tmem, static_cast<uint32_t>(a.tmem_cols));
     if ((a.timeline & 1) && blockIdx.x == 0 && lane == 0) g_timeline[507] = clock64();
     if ((a.timeline & 4) && lane == 0) atomicMax(&g_span[a.launch_id & 63][1], globaltimer_ns());
+    // bit 3: exit time of every CTA (ns since the first CTA of this launch entered; needs bit 2 as well)
+    if ((a.timeline & 8) && lane == 0 && blockIdx.x < 512)
+      g_timeline[blockIdx.x] = static_cast<long long>(globaltimer_ns() - g_span[a.launch_id & 63][0]);
   }
 }
 
