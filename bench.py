@@ -209,10 +209,13 @@ def run_ours(args):
     rank, world, local = rank_world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    # stdout carries exactly one JSON line: anything libraries print on file descriptor 1 meanwhile (NCCL's version
+    # banner, for one) is sent to stderr, and the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -360,7 +363,8 @@ def run_ours(args):
                 "steps_per_sec": K / (ms * 1e-3), "sr_images_per_sec": value / (NOISE_STEPS - 1),
                 "clocks": clock_info, "e2e": e2e, "gpu_launches": K * launches_per_step,
                 "launches_per_step": launches_per_step, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
