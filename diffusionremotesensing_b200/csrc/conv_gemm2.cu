@@ -171,6 +171,26 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       }
       int st = 0, sub_first = 0, sub_cnt = 0;
       TL(pno, 0);
+      if (a.l2_prefetch) {
+        // Pull the halo tiles of the pair AFTER this one into L2 now: the A ring only holds about half a pair, so
+        // without this every tile load pays the full HBM latency on the layers whose inputs exceed L2.
+        const int nt0 = tile0 + 2 * tile_step;
+        if (elect_one()) {
+          for (int p = 0; p < 2; ++p) {
+            const int tile = nt0 + p * tile_step;
+            if (tile < a.n_tiles) {
+              const int nb_ = tile / tiles_per_img;
+              const int t2 = tile - nb_ * tiles_per_img;
+              const int ny = (t2 / a.tiles_x) * kTile2H, nx = (t2 % a.tiles_x) * kTile2W;
+              for (int s2 = 0; s2 < a.n_sub_tiles; ++s2) {
+                const SubTile T = prog.st[s2];
+                tma_prefetch_5d(T.src ? &map1 : &map0, T.c, nx + T.dx0, 0, ny + T.dy0, nb_);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
       for (int kb = 0; kb < nkb; ++kb) {
         const KB3 K = prog.kb[kb];
         if (K.flags & KB2_FIRST) {

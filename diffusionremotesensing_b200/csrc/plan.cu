@@ -228,6 +228,9 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   static const bool no_solo = (getenv("DRS_V2_NO_SOLO") != nullptr);
   a.solo = (!no_solo && g.epi_kind == EPI_STD && a.acc_bufs == 1 && g.n_groups >= 2 && g.n_groups % 2 == 0) ? 1 : 0;
   a.err = p->d_err;
+  // L2 prefetch of the next pair's tiles (DRS_V2_L2_PREFETCH=1): measured +4 % step time at cfg 2, off by default
+  static const int l2pf = getenv("DRS_V2_L2_PREFETCH") ? atoi(getenv("DRS_V2_L2_PREFETCH")) : 0;
+  a.l2_prefetch = l2pf;
   static const int timeline = getenv("DRS_V2_TIMELINE") ? atoi(getenv("DRS_V2_TIMELINE")) : 0;
   // bit 0: record stamps, bit 1: skip the epilogue body (timing experiments only); DRS_V2_TIMELINE_LAYER restricts
   // the recording to launches whose name contains the given substring
