@@ -212,14 +212,21 @@ __device__ __forceinline__ void conv_epilogue(const EpiArgs& e, uint32_t taddr, 
     for (int c0 = 0; c0 < N; c0 += 16) {
       float v[16];
       tmem_ld16(taddr + c0, v);
+      // per-channel vectors as 128-bit loads (shared-memory bandwidth is what bounds this kernel): scale, bias and
+      // one float4 of the (up to four) output-conv weights per channel, zero beyond nvec
+      float sc[16], bi[16];
+      ld16_shared(&s_par[0][c0], sc);
+      ld16_shared(&s_par[1][c0], bi);
       tmem_ld_wait();
+      const float4* wq = reinterpret_cast<const float4*>(&s_par[2][0]) + c0;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const int c = c0 + i;
-        const float t = fmaf(v[i], s_par[0][c], s_par[1][c]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < e.nvec) acc[k] = fmaf((&s_par[2][0])[k * N + c], t, acc[k]);
+        const float t = fmaf(v[i], sc[i], bi[i]);
+        const float4 w4 = wq[i];
+        acc[0] = fmaf(w4.x, t, acc[0]);
+        acc[1] = fmaf(w4.y, t, acc[1]);
+        acc[2] = fmaf(w4.z, t, acc[2]);
+        acc[3] = fmaf(w4.w, t, acc[3]);
       }
     }
     if (valid) {
@@ -427,9 +434,14 @@ __device__ __forceinline__ void load_epilogue_params(const EpiArgs& e, int n_sub
       s_par[3][c] = e.bias2 ? __ldg(e.bias2 + oc_off + c) : 0.0f;
     }
   }
-  if (EPI != EPI_STD) {
-    const int nw = (EPI == EPI_PSI) ? n_sub : e.nvec * n_sub;
-    for (int c = tid; c < nw; c += nthreads) (&s_par[2][0])[c] = __ldg(e.wvec + c);
+  if (EPI == EPI_PSI) {
+    for (int c = tid; c < n_sub; c += nthreads) (&s_par[2][0])[c] = __ldg(e.wvec + c);
+  } else if (EPI == EPI_OUT) {
+    // output-conv weights interleaved per channel: [c][k], k < 4, zero for k >= nvec (n_sub <= 128)
+    for (int i = tid; i < 4 * n_sub; i += nthreads) {
+      const int c = i >> 2, k = i & 3;
+      (&s_par[2][0])[i] = (k < e.nvec) ? __ldg(e.wvec + k * n_sub + c) : 0.0f;
+    }
   }
 }
 
