@@ -1,0 +1,70 @@
+"""Size-independent properties checked at BASELINE.json's full size (cfg 2: superres x2, LR 128 -> 256, n = 16), where
+the CPU oracle would need minutes per evaluation:
+
+  * a sample's result does not depend on what else is in the batch: the first two samples of the 16-image evaluation
+    are bit-identical to a 2-image evaluation (different plan, different tile -> CTA assignment, same arithmetic);
+  * every kernel path (CTA pair on / off / everywhere, staged or per-thread stores, solo drain, programmatic dependent
+    launch, gate branch on a side stream) produces bit-identical eps and a bit-identical 3-step trajectory.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import common as T
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_batch_independence_at_full_size(cuda_device):
+    n, S = 16, 256
+    m, sd = T.default_init_model("superres")
+    m.to(cuda_device).eval()
+    lr = T.np_rand(2, 1, 3, S // 2, S // 2).to(cuda_device)
+    x = T.np_randn(3, n, 3, S, S).to(cuda_device)
+    t = torch.full((n,), 700, device=cuda_device)
+    with torch.no_grad():
+        full = m(x, t, lr, 2).clone()
+        part = m(x[:2].contiguous(), t[:2], lr, 2).clone()
+    assert torch.isfinite(full).all()
+    assert torch.equal(full[:2], part), "a sample's eps changed with the batch it was evaluated in"
+
+
+def digest(env):
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "full_size_digest.py")], cwd=ROOT, env=e,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith(("eps ", "x3 "))]
+    assert len(lines) == 2 and lines[1].endswith("finite True"), r.stdout[-2000:]
+    return lines
+
+
+def test_kernel_paths_bit_identical_at_full_size(cuda_device):
+    base = digest({})
+    for env in ({"DRS_CG2": "none"}, {"DRS_CG2": "all"}, {"DRS_V2_NO_TMA_STORE": "1"}, {"DRS_V2_NO_SOLO": "1"},
+                {"DRS_V2_NO_PDL": "1", "DRS_NO_FORK": "1"}):
+        assert digest(env) == base, f"{env} changed the result"
+
+
+def test_full_resolution_eps_matches_oracle(cuda_device):
+    """One 256 x 256 sample against the CPU fp32 oracle (a few seconds of CPU time); together with batch independence
+    this covers the eps of the whole cfg-2 batch. Tolerance: north_star's 2e-2 max relative error."""
+    from oracle import restatement as R
+    S = 256
+    m, sd = T.default_init_model("superres")
+    m.to(cuda_device).eval()
+    lr = T.np_rand(2, 1, 3, S // 2, S // 2)
+    x = T.np_randn(3, 1, 3, S, S)
+    t = torch.full((1,), 700)
+    with torch.no_grad():
+        ref = R.unet_forward(sd, "superres", x, t, lr, 2)
+        got = m(x.to(cuda_device), t.to(cuda_device), lr.to(cuda_device), 2).cpu()
+    err = T.max_rel_err(got, ref)
+    print(f"full-resolution eps max rel err {err:.2e}")
+    assert err <= 2e-2
