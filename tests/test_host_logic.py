@@ -157,3 +157,43 @@ def test_patch_sharding_and_gather_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_bench_clock_sampler_filters_samples_to_the_timed_region(tmp_path):
+    """bench.py's nvidia-smi reader: samples are kept by timestamp window, throttle reasons are collected, and a region
+    shorter than the sampling period falls back to every sample taken during the run."""
+    import datetime
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("drs_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeProc:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+
+    t0 = datetime.datetime(2026, 1, 1, 12, 0, 0).timestamp()
+    rows = [(t0 + 0.1, 1200, "Not Active"), (t0 + 1.1, 1965, "Not Active"), (t0 + 1.2, 1950, "Active"),
+            (t0 + 2.5, 900, "Not Active")]
+    path = tmp_path / "clocks.csv"
+    with open(path, "w") as f:
+        for ts, mhz, cap in rows:
+            stamp = datetime.datetime.fromtimestamp(ts).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+            f.write(f"{stamp}, {mhz}, 1965, Not Active, Not Active, Not Active, {cap}\n")
+
+    def sampler():
+        s = bench.ClockSampler.__new__(bench.ClockSampler)
+        s.proc, s.path, s.f = FakeProc(), str(path), open(path, "a")
+        return s
+
+    out = sampler().stop(t0 + 1.0, t0 + 2.0)
+    assert out["samples"] == 2 and out["sm_mhz"] == 1957.5 and out["sm_max_mhz"] == 1965
+    assert out["reasons"] == ["sw_power_cap"] and out["window"] == "timed region"
+    # (stop() removes the file: write it again for the fallback case)
+    with open(path, "w") as f:
+        stamp = datetime.datetime.fromtimestamp(t0 + 5.0).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+        f.write(f"{stamp}, 1500, 1965, Not Active, Not Active, Not Active, Not Active\n")
+    out = sampler().stop(t0 + 1.0, t0 + 1.001)
+    assert out["samples"] == 1 and out["sm_mhz"] == 1500 and out["window"].startswith("whole run")
