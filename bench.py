@@ -238,10 +238,14 @@ def run_ours(args):
     N.check(lib.drs_cond_encode(plan, N.ptr(lr_dev), st))
     N.check(lib.drs_sampler_prepare(plan, NOISE_STEPS, N.ptr(c1), N.ptr(c2), N.ptr(c3), None, 0.0, st))
     N.check(lib.drs_sampler_begin(plan, N.ptr(x), N.ptr(z), N.ptr(eps), NOISE_STEPS - 1, st))
-    if K + W > NOISE_STEPS - 2:
-        raise SystemExit("steps + warmup must stay below the 1499 UNet evaluations of the schedule")
+    left = [NOISE_STEPS - 2]   # noisy steps before the chain reaches its last (noise-free) step
 
     def step():
+        if left[0] <= 0:
+            # more steps requested than one 1499-evaluation chain holds: start the next chain on the same state
+            N.check(lib.drs_sampler_begin(plan, N.ptr(x), N.ptr(z), N.ptr(eps), NOISE_STEPS - 1, st))
+            left[0] = NOISE_STEPS - 2
+        left[0] -= 1
         z.normal_()
         N.check(lib.drs_sampler_step(plan, 1, st))
 
