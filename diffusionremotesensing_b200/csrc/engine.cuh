@@ -132,6 +132,8 @@ struct DrsModel {
   drs::TimeMlp mlps[7];                          // conv_blocks.0-2, bottle_neck, ups.0-2
   int te_stride = 0;
   long inv_freq = -1, label_emb = -1;
+  int n_layers = 0;            // gemms[0 .. n_layers) are the layers, the rest their narrow (32-channel) variants
+  std::vector<int> alt;        // alt[i]: index of layer i's narrow variant in gemms, or -1
   drs::SmallConv conv0, enc[7], cond_conv;       // enc: blocks.{0,1,2}.conv{1,2}, conv_out
   bool has_cond = false;
 

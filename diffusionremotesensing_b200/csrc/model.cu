@@ -152,8 +152,29 @@ struct Builder {
     return true;
   }
 
-  // Appends the K-blocks of `terms` for every N-split and packs the weight tiles.
+  // Narrow variants (32 output channels per CTA) of the launches whose wide form leaves most SMs idle on small grids:
+  // same terms, same epilogue, four (or more) times as many CTAs, each streaming a quarter of the weights. The plan
+  // picks the variant per launch (plan.cu); a variant is found through its name.
+  std::vector<GemmSpec> narrow;
+
   bool build(GemmSpec& g, const std::vector<ConvTerm>& terms) {
+    if (!build_one(g, terms)) return false;
+    static const bool no_narrow = (getenv("DRS_NO_NARROW") != nullptr);
+    if (!no_narrow && g.epi_kind == EPI_STD && g.n_sub >= 64 && g.OC % 32 == 0 && !(g.flags & F_DUAL_POST)) {
+      GemmSpec n = g;
+      n.kblocks.clear();
+      n.v2 = GemmSpec::V2();
+      n.max_a_bytes = n.max_b_bytes = 0;
+      n.n_sub = 32;
+      if (n.flags & F_DUAL_PRE) n.col2 = n.n_sub;
+      if (build_one(n, terms)) narrow.push_back(std::move(n));
+      else return false;
+    }
+    return true;
+  }
+
+  // Appends the K-blocks of `terms` for every N-split and packs the weight tiles.
+  bool build_one(GemmSpec& g, const std::vector<ConvTerm>& terms) {
     g.nsplit = g.OC / g.n_sub;
     if (g.nsplit * g.n_sub != g.OC || g.n_sub % 16) {
       set_error("%s: bad split OC=%d n_sub=%d", g.name.c_str(), g.OC, g.n_sub);
@@ -539,6 +560,18 @@ static bool build_small(Builder& B, const std::string& p, int cout, int cin, Sma
   return true;
 }
 
+// Appends the narrow variants after the layers and links each layer to its variant (by name).
+static void append_narrow(DrsModel* m, Builder& B) {
+  m->n_layers = static_cast<int>(m->gemms.size());
+  m->alt.assign(m->gemms.size(), -1);
+  for (GemmSpec& n : B.narrow) {
+    for (int i = 0; i < m->n_layers; ++i)
+      if (m->gemms[i].name == n.name) m->alt[i] = static_cast<int>(m->gemms.size());
+    m->gemms.push_back(std::move(n));
+  }
+  B.narrow.clear();
+}
+
 static bool build_model(DrsModel* m) {
   Builder B(m);
   const DrsModelDesc& d = m->desc;
@@ -784,6 +817,7 @@ static bool build_model(DrsModel* m) {
     }
     xin = "x" + si;
   }
+  append_narrow(m, B);
   return true;
 }
 
@@ -859,6 +893,7 @@ int build_debug_conv(DrsModel* m, const float* w, const float* bias, const float
   }
   if (!B.build(g, {term(0, Cin, kind, {wr})})) return DRS_E_INVALID;
   m->gemms.push_back(std::move(g));
+  append_narrow(m, B);
   DRS_TRY(m->d_fblob.upload(m->fblob.data(), m->fblob.size() * sizeof(float)));
   DRS_TRY(m->d_wblob.upload(m->wblob.data(), m->wblob.size()));
   DRS_TRY(m->d_kblocks.upload(m->kb_all.data(), m->kb_all.size() * sizeof(KBlock)));

@@ -507,7 +507,21 @@ int plan_create(DrsModel* m, int nb, int nx, int ncond, int S, int mag, DrsPlan*
 
   // launch list
   uint8_t* ws = p->workspace.as<uint8_t>();
-  for (size_t gi = 0; gi < m->gemms.size(); ++gi) {
+  const size_t n_layers = m->n_layers > 0 ? static_cast<size_t>(m->n_layers) : m->gemms.size();
+  for (size_t li = 0; li < n_layers; ++li) {
+    // Small grids: when the wide form of a launch would occupy less than half of the SMs, its narrow variant (32 output
+    // channels per CTA) spreads the K loop and the weight streaming over four or more times as many CTAs.
+    size_t gi = li;
+    {
+      const GemmSpec& w = m->gemms[li];
+      const ActTensor& s0w = p->acts.at(w.src_name[0]);
+      const int gh = w.src_stride2[0] ? s0w.H / 2 : s0w.H, gw = w.src_stride2[0] ? s0w.W / 2 : s0w.W;
+      const long tiles = static_cast<long>(p->nb) * ((gh + kTile2H - 1) / kTile2H) * ((gw + kTile2W - 1) / kTile2W);
+      static const int narrow_below = getenv("DRS_NARROW_BELOW") ? atoi(getenv("DRS_NARROW_BELOW")) : 74;
+      const long ctas_wide = ((tiles + 1) / 2) * w.nsplit;
+      if (li < m->alt.size() && m->alt[li] >= 0 && gh >= kTile2H && gw >= kTile2W && ctas_wide < narrow_below)
+        gi = static_cast<size_t>(m->alt[li]);
+    }
     const GemmSpec& g = m->gemms[gi];
     const ActTensor& s0 = p->acts.at(g.src_name[0]);
     const void* src[2] = {ws + s0.offset, nullptr};
