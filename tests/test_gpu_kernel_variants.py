@@ -7,6 +7,7 @@ path (tests/test_gpu_conv_layers.py):
   * DRS_V2_GENERIC_EPILOGUE run-time flag epilogue instead of the compile-time variants
   * DRS_V2_NO_SOLO=1        transposed convolutions drained by one epilogue group per tile
   * DRS_DISABLE_V2=1        first-generation kernel for every layer
+  * DRS_NO_NARROW=1         no 32-channel launch variants on small grids (the default test sizes otherwise use them)
 """
 import os
 import subprocess
@@ -47,3 +48,8 @@ def test_cta_pair_kernel_unet_and_sampler_parity(cuda_device):
     r = run_child({"DRS_CG2": "all"}, ["tests/test_gpu_unet.py", "tests/test_gpu_sampler.py"])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "CTA-pair kernel" in r.stderr or "CTA-pair kernel" in r.stdout
+
+
+def test_unet_parity_without_narrow_variants(cuda_device):
+    r = run_child({"DRS_NO_NARROW": "1"}, ["tests/test_gpu_unet.py"])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
