@@ -15,8 +15,17 @@ its own GPU (weak scaling, no data-path collective).
              preparation, K graph-replayed steps, D2H of the samples -- all inside the timed region
   roofline   tensor-core bound: algorithmic conv FLOPs of one UNet evaluation / CUDA-event time of the chain of
              tcgen05 implicit-GEMM launches of one forward (drs_plan_time_forward: events around the chain on the
-             launching stream), against MEASURED_PEAKS.json bf16_tflops_sustained; `traffic` = DRAM bytes per launch
-             from the committed ncu capture (profiles/ncu_traffic.json)
+             launching stream). Both fractions are printed -- frac_sustained (MEASURED_PEAKS.json
+             bf16_tflops_sustained: a 4 s back-to-back cuBLAS run that pulls the clock down) and frac_burst
+             (bf16_tflops: best single GEMM at full clock); `frac` is the one that matches this run's own clock record
+             (SM clock at its maximum and no power cap -> burst). `traffic` = DRAM bytes per launch from the committed
+             ncu capture (profiles/ncu_traffic.json).
+             roofline.hbm_kernels: the HBM-bound kernels of the path -- conv0, the posterior update (both at cfg 2) and
+             the aggregation blend (cfg-5 shape, 961 patches -> 3 x 4096 x 4096) -- algorithmic bytes / CUDA-event
+             time on a flushed L2 / MEASURED_PEAKS.json hbm_gbs
+  aggregation  cfg 5 as a STRONG-scaling leg: the 961 overlapping 128 -> 256 patches of an LR 2048 x 2048 scene, block
+             partitioned over the N ranks, sampled for min(K, 50) reverse steps, gathered to rank 0 (NCCL) and blended
+             there; seconds = max over ranks of the whole thing (gather and blend inside the timed region)
   cpu_baseline  the reference algorithm (oracle port: the same torch CPU ops the reference's modules call) timed on
              this box's host cores on a bounded sample of the same workload
 
@@ -34,7 +43,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "unet_denoise_image_steps_per_sec"
 UNIT = "image-steps/s"
@@ -54,9 +62,10 @@ def measured_peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return {"tflops": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops"))), "hbm_gbs": float(p["hbm_gbs"]),
-                "source": "MEASURED_PEAKS.json bf16_tflops_sustained"}
-    return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md, sustained)"}
+        return {"tflops": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops"))),
+                "tflops_burst": float(p.get("bf16_tflops", p.get("bf16_tflops_sustained"))),
+                "hbm_gbs": float(p["hbm_gbs"]), "source": "MEASURED_PEAKS.json"}
+    return {"tflops": 1400.0, "tflops_burst": 1650.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
@@ -129,7 +138,7 @@ class ClockSampler:
 
 def synthetic_model_and_inputs():
     import torch
-    import common as T
+    from diffusionremotesensing_b200 import synthetic as T
     model, sd = T.default_init_model("superres", seed=0, bn_seed=1)
     lr = T.np_rand(2, 3, S // MAG, S // MAG)       # Sentinel-2-shaped RGB in [0, 1)
     return model, sd, lr
@@ -141,9 +150,12 @@ def synthetic_model_and_inputs():
 def cpu_reference_arm(steps, warmup, budget_s, n_images=None):
     """Times `steps` reverse steps of the oracle port on n_images of the 16-image batch (bounded sample)."""
     import torch
-    import common as T
+    from diffusionremotesensing_b200 import synthetic as T
     from oracle import restatement as R
     torch.set_grad_enabled(False)
+    # all host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, which must not reach the CPU arm
+    host_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, host_cores))
     cores = torch.get_num_threads()
     _, sd, lr = synthetic_model_and_inputs()
     sched = R.noise_schedule("cosine", NOISE_STEPS)
@@ -198,10 +210,92 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
+SCENE_ARG = [2048]
+
+
+def aggregation_leg(model, dev, k_steps, rank, world, roofline):
+    """cfg 5 (Aggregation_Sampling.py:94-110): the 961 overlapping 128 -> 256 patches of an LR 2048 x 2048 scene.
+    The row-major patch list is block-partitioned over the ranks; every rank samples its block in equal batches
+    (k_steps reverse steps of a (k_steps + 1)-step cosine schedule), one gather brings the SR patches to rank 0, which
+    blends them. Timed from the first patch to the blended scene, max over ranks: a fixed amount of work whatever N."""
+    import torch
+    import torch.distributed as dist
+    from diffusionremotesensing_b200 import synthetic as T
+    import diffusionremotesensing_b200 as D
+    from diffusionremotesensing_b200.aggregation import blend_patches, gather_blocks, partition_blocks
+    side, P, stride, k = SCENE_ARG[0], 128, 64, MAG
+    scene = T.np_rand(7, 1, 3, side, side).to(dev)
+    d = D.Diffusion("cosine", model, "/nonexistent", noise_steps=k_steps + 1, device=str(dev),
+                    magnification_factor=k, image_size=P * k, Degradation_type="DownBlur")
+    agg = D.split_aggregation_sampling(scene, P, stride, k, d, str(dev), patch_batch=32)
+    n = len(agg.patches_lr)
+    blocks = partition_blocks(n, world)
+    counts = [b - a for a, b in blocks]
+    lo, hi = blocks[rank]
+    n_batches = max(1, -(-(hi - lo) // agg.patch_batch))
+    size = -(-(hi - lo) // n_batches)
+    # warm-up: one batch of this rank's batch size builds its plan, time table and CUDA graphs
+    agg.sample_patches(range(lo, min(hi, lo + size)), private_rng=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    local = agg.sample_patches(range(lo, hi), private_rng=True)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    patches = gather_blocks(local, counts, dst=0) if world > 1 else local
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    H = W = side * k
+    blend_ms = None
+    if rank == 0:
+        w2d = agg.weight[0, 0].contiguous()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out, wsum = blend_patches(patches, agg.patches_sr_infos, w2d, H, W, clamp=True)
+        e1.record()
+        torch.cuda.synchronize()
+        blend_ms = e0.elapsed_time(e1)
+        assert torch.isfinite(out).all()
+    t3 = time.perf_counter()
+    tt = torch.tensor([t3 - t0, t1 - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total, sample_s = float(tt[0]), float(tt[1])
+    res = {"workload": f"cfg 5: LR {side}x{side} scene -> {n} patches {P}->{P * k}, stride {stride}, "
+                       f"{k_steps} reverse steps per patch", "scaling": "strong", "patches": n, "steps": k_steps,
+           "n_gpus": world, "patches_per_rank": counts, "patch_batch": size, "seconds": total,
+           "sample_seconds_max_rank": sample_s, "gather_ms": (t2 - t1) * 1e3, "blend_ms": blend_ms,
+           "image_steps_per_sec": n * k_steps / total,
+           "note": "seconds = first patch to blended scene on rank 0, max over ranks; gather_ms / blend_ms are rank 0's"}
+    if rank == 0 and roofline is not None:
+        # blend kernel on a flushed L2, cache-hit call (no table upload): algorithmic bytes = patches in + scene and
+        # weight-sum map out (Aggregation_Sampling.py:96-110 materialises pixel_count too)
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+        times = []
+        for i in range(5):
+            flush.fill_(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            blend_patches(patches, agg.patches_sr_infos, w2d, H, W, clamp=True)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms_b = min(times[1:])
+        by = float(patches.numel() * 4 + 3 * H * W * 4 + H * W * 4)
+        hbm = roofline["hbm_kernels"]["peak_gbs"]
+        roofline["hbm_kernels"]["blend_gather4_kernel"] = {
+            "bytes": by, "ms": ms_b, "gbs": by / (ms_b * 1e6), "frac": by / (ms_b * 1e6) / hbm,
+            "what": f"{n} SR patches [3,{P * k},{P * k}] fp32 in, scene [3,{H},{W}] + weight-sum map out "
+                    "(cfg-5 shape), best of 4 after one warm call, 512 MB L2 flush before each"}
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    import common as T
+    from diffusionremotesensing_b200 import synthetic as T
     import diffusionremotesensing_b200 as D
     from diffusionremotesensing_b200 import _native as N
     import ctypes as C
@@ -311,16 +405,49 @@ def run_ours(args):
             with open(tpath) as f:
                 tj = json.load(f)
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_source": traffic_src,
+        # which measured peak matches THIS run: the sustained figure belongs to a power-limited clock; a run whose SM
+        # clock sat at its maximum with no power cap is compared with the burst figure
+        at_max_clock = bool(clock_info and clock_info.get("sm_mhz") and clock_info.get("sm_max_mhz") and
+                            clock_info["sm_mhz"] >= 0.97 * clock_info["sm_max_mhz"] and
+                            "sw_power_cap" not in clock_info.get("reasons", []))
+        frac_s, frac_b = achieved / peaks["tflops"], achieved / peaks["tflops_burst"]
+        # HBM-bound kernels: conv0 and the posterior update at cfg 2, each launch on a flushed L2
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+        ms_h = torch.zeros(2, dtype=torch.float32)
+        N.check(lib.drs_sampler_begin(plan, N.ptr(x), N.ptr(z), N.ptr(eps), NOISE_STEPS - 1, st))
+        N.check(lib.drs_sampler_time_hbm_kernels(plan, N.ptr(flush), flush.numel(), 20, N.ptr(ms_h), st))
+        left[0] = NOISE_STEPS - 2
+        hbm = peaks["hbm_gbs"]
+        name0 = C.create_string_buffer(64)
+        by0 = C.c_double()
+        N.check(lib.drs_plan_launch_info(plan, 0, name0, 64, None, C.byref(by0), None, None))
+        upd_bytes = 16.0 * x.numel()     # read x, eps, z; write x (fp32)
+        hbm_kernels = {
+            "conv0_kernel": {"bytes": by0.value, "ms": float(ms_h[0]), "gbs": by0.value / (float(ms_h[0]) * 1e6),
+                             "frac": by0.value / (float(ms_h[0]) * 1e6) / hbm,
+                             "what": "x fp32 NCHW + condition feature in, h0 bf16 NHWC out (cfg 2)"},
+            "ddpm_update_kernel": {"bytes": upd_bytes, "ms": float(ms_h[1]), "gbs": upd_bytes / (float(ms_h[1]) * 1e6),
+                                   "frac": upd_bytes / (float(ms_h[1]) * 1e6) / hbm,
+                                   "what": "16 B per element: x, eps, z in, x out (cfg 2), bookkeeping tail included"},
+            "peak_gbs": hbm, "timing": "CUDA events around single launches, 512 MB L2 flush before each, mean of 20"}
+        del flush
+        roofline = {"bound": "tensor", "achieved": achieved, "unit": "TFLOP/s",
+                    "peak": peaks["tflops_burst"] if at_max_clock else peaks["tflops"],
+                    "frac": frac_b if at_max_clock else frac_s,
+                    "peak_kind": ("burst (bf16_tflops): SM clock at max, no power cap during the timed region"
+                                  if at_max_clock else "sustained (bf16_tflops_sustained)"),
+                    "frac_sustained": frac_s, "frac_burst": frac_b,
+                    "peak_sustained": peaks["tflops"], "peak_burst": peaks["tflops_burst"],
+                    "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peaks["source"],
-                    "kernel": f"conv_gemm2_kernel (the {n_conv} tcgen05 implicit-GEMM launches of one UNet evaluation)",
+                    "kernel": f"conv_gemm kernels (the {n_conv} tcgen05 implicit-GEMM launches of one UNet evaluation)",
                     "launches_per_eval": n_conv,
                     "algorithmic_gflop_per_eval": tot_f / 1e9, "algorithmic_gflop_per_launch": tot_f / 1e9 / n_conv,
                     "kernel_ms_per_eval": chain_ms, "kernel_ms_per_launch": chain_ms / n_conv,
                     "conv0_ms": float(ms2[0]),
                     "kernel_share_of_step": chain_ms / (ms / K),
-                    "per_launch_event_sum_ms": tot_ms}
+                    "per_launch_event_sum_ms": tot_ms,
+                    "hbm_kernels": hbm_kernels}
         if args.layers:
             with open(args.layers, "w") as f:
                 json.dump(layer_rows, f, indent=1)
@@ -351,6 +478,11 @@ def run_ours(args):
            "call": f"Diffusion.sample(n={BATCH}, model, lr_img) with noise_steps={K + 1} ({K} UNet evaluations), pinned host in/out",
            "seconds": dt}
 
+    # ---- cfg 5: aggregation sampling of an LR 2048 x 2048 scene, patch list sharded over the ranks (strong scaling) ----
+    aggregation = None
+    if not args.no_aggregation:
+        aggregation = aggregation_leg(model, dev, min(K, 50), rank, world, roofline)
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -366,7 +498,8 @@ def run_ours(args):
                            "parallelism": f"batch-sharded x{world}, no per-step collective"},
                 "steps_per_sec": K / (ms * 1e-3), "sr_images_per_sec": value / (NOISE_STEPS - 1),
                 "clocks": clock_info, "e2e": e2e, "gpu_launches": K * launches_per_step,
-                "launches_per_step": launches_per_step, "roofline": roofline, "cpu_baseline": cpu}
+                "launches_per_step": launches_per_step, "roofline": roofline, "aggregation": aggregation,
+                "cpu_baseline": cpu}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -382,9 +515,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", default=None, help="write the per-launch table (JSON) to this path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-aggregation", action="store_true", help="skip the cfg-5 aggregation (strong-scaling) leg")
+    ap.add_argument("--scene", type=int, default=2048, help="LR scene side of the aggregation leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    SCENE_ARG[0] = args.scene
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -9,7 +9,8 @@ from .diffusion import Diffusion, Diffusion_SAR_TO_NDVI, Diffusion_generation
 from .aggregation import split_aggregation_sampling, partition_blocks, gather_blocks, blend_patches
 
 from .entrypoints import (super_resolver, SAR_to_NDVI_generator, generate_per_class, prepare_scene,
-                          aggregation_super_resolver, parse_model_name, normalise_sar)
+                          aggregation_super_resolver, parse_model_name, normalise_sar, load_scene, save_scene,
+                          nearest_scene_size, launch)
 
 Diffusion_superres = Diffusion
 
@@ -18,5 +19,5 @@ __all__ = [
     "Diffusion", "Diffusion_superres", "Diffusion_SAR_TO_NDVI", "Diffusion_generation",
     "split_aggregation_sampling", "partition_blocks", "gather_blocks", "blend_patches",
     "super_resolver", "SAR_to_NDVI_generator", "generate_per_class", "prepare_scene", "aggregation_super_resolver",
-    "parse_model_name", "normalise_sar",
+    "parse_model_name", "normalise_sar", "load_scene", "save_scene", "nearest_scene_size", "launch",
 ]

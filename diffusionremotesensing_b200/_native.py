@@ -59,6 +59,7 @@ SIGNATURES = {
                                        C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "drs_plan_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "drs_plan_time_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "drs_sampler_time_hbm_kernels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "drs_ddpm_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_size_t,
                                   C.c_void_p]),
     "drs_noise_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t,
@@ -67,14 +68,21 @@ SIGNATURES = {
                             C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "drs_debug_conv2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "drs_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "drs_debug_mma_rate2": (C.c_int, [C.c_int] * 7 + [C.c_void_p]),
     "drs_debug_timeline": (C.c_int, [C.c_void_p, C.c_int]),
     "drs_debug_spans": (C.c_int, [C.c_void_p, C.c_int]),
     "drs_debug_fetch": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
+# include/drs_b200_diag.h, part 1: the separate diagnostics library (micro-benchmarks; never on the product path)
+DIAG_LIB_PATH = os.path.join(_HERE, "libdrs_b200_diag.so")
+DIAG_SIGNATURES = {
+    "drs_diag_last_error": (C.c_char_p, []),
+    "drs_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "drs_debug_mma_rate2": (C.c_int, [C.c_int] * 7 + [C.c_void_p]),
+}
+
 _lib: Optional[C.CDLL] = None
+_diag: Optional[C.CDLL] = None
 
 
 def build(verbose: bool = False) -> str:
@@ -101,6 +109,27 @@ def lib() -> C.CDLL:
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+def diag_lib() -> C.CDLL:
+    """libdrs_b200_diag.so (scripts/diag_mma_rate*.py only)."""
+    global _diag
+    if _diag is None:
+        if not os.path.exists(DIAG_LIB_PATH):
+            raise ImportError(f"{DIAG_LIB_PATH} is missing: build it with `make -C {CSRC}`")
+        handle = C.CDLL(DIAG_LIB_PATH)
+        for name, (res, args) in DIAG_SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _diag = handle
+    return _diag
+
+
+def check_diag(code: int) -> None:
+    if code != 0:
+        msg = diag_lib().drs_diag_last_error()
+        raise DrsError(code, msg.decode("utf-8", "replace") if msg else "unknown error")
 
 
 def check(code: int) -> None:

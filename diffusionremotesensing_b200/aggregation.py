@@ -8,7 +8,11 @@ Same constructor, public attributes (``patches_lr``, ``patches_sr_infos``, ``wei
     cross-sample statistics);
   * with ``torch.distributed`` initialised the row-major patch list is block-partitioned over the ranks, each rank
     samples its block on its own GPU, one gather brings the finished patches to rank 0, which blends them in the
-    reference's patch order (so the blend is bit-identical whatever the world size) and broadcasts the scene;
+    reference's patch order and broadcasts the scene. The BLEND is bit-identical whatever the world size; the whole
+    scene is bit-identical across world sizes only with injected noise (``noise=`` / ``x_T=`` hooks): without them
+    every rank draws from private generators seeded ``torch.initial_seed() + 1 + first patch index of its block`` so
+    that identically seeded ranks do not reuse one noise stream for different patches (the reference's sequential
+    per-patch RNG stream cannot be reproduced by concurrent chains);
   * the Gaussian overlap blend, the division and the clamp are one CUDA kernel (``drs_blend``) that accumulates
     each output pixel in patch order with separately rounded fp32 multiply and add, like the reference's
     ``im_res[...] += patch_sr * weight`` sequence.
@@ -127,17 +131,39 @@ class split_aggregation_sampling:
 
     # -- sampling ------------------------------------------------------------------------------------------------
     def sample_patches(self, indices: Sequence[int], noise: Optional[Callable] = None,
-                       x_T: Optional[Callable] = None) -> torch.Tensor:
-        """SR patches [len(indices), C, P*k, P*k] for the given patch indices, in batches of `patch_batch`.
-        noise(patch_index, step) / x_T(patch_index) inject per-patch noise (parity tests)."""
-        outs = []
+                       x_T: Optional[Callable] = None, private_rng: bool = False) -> torch.Tensor:
+        """SR patches [len(indices), C, P*k, P*k] for the given patch indices.
+        The block is cut into ceil(n / patch_batch) batches of ONE size (the shorter ones are padded by repeating
+        their last patch; the duplicate is dropped), so a single plan, time table and pair of CUDA graphs serve the
+        whole block (121 patches, patch_batch 32 -> 4 batches of 31). An empty block returns [0, C, P*k, P*k].
+        noise(patch_index, step) / x_T(patch_index) inject per-patch noise (parity tests); private_rng draws from
+        generators seeded by the block's first patch index instead of the global ones (sharded runs)."""
+        indices = list(indices)
+        k = self.magnification_factor
+        channels = self.img_lr.shape[1]
+        side = self.patch_size * k
+        if not indices:
+            return torch.empty((0, channels, side, side), device=self.device, dtype=torch.float32)
         dm = self.diffusion_model
-        for b0 in range(0, len(indices), self.patch_batch):
-            idx = list(indices[b0:b0 + self.patch_batch])
+        n = len(indices)
+        n_batches = -(-n // self.patch_batch)
+        size = -(-n // n_batches)
+        gen = cpu_gen = None
+        if private_rng and noise is None:
+            seed = torch.initial_seed() + 1 + indices[0]
+            gen = torch.Generator(device=self.device).manual_seed(seed)
+            cpu_gen = torch.Generator().manual_seed(seed)
+        outs = []
+        for b0 in range(0, n, size):
+            idx = indices[b0:b0 + size]
+            real = len(idx)
+            idx = idx + [idx[-1]] * (size - real)
             lr = torch.cat([self.patches_lr[i] for i in idx], dim=0).to(self.device)
             xt = None if x_T is None else torch.cat([x_T(i) for i in idx], dim=0)
             nz = None if noise is None else (lambda step, idx=idx: torch.cat([noise(i, step) for i in idx], dim=0))
-            outs.append(dm.sample_batched(self.model, lr, input_channels=lr.shape[1], x_T=xt, noise=nz))
+            sr = dm.sample_batched(self.model, lr, input_channels=lr.shape[1], x_T=xt, noise=nz, generator=gen,
+                                   cpu_generator=cpu_gen)
+            outs.append(sr[:real])
         return torch.cat(outs, dim=0)
 
     def aggregation_sampling(self, noise: Optional[Callable] = None, x_T: Optional[Callable] = None, group=None):
@@ -152,7 +178,7 @@ class split_aggregation_sampling:
             rank, world = dist.get_rank(group), dist.get_world_size(group)
             blocks = partition_blocks(n, world)
             lo, hi = blocks[rank]
-            local = self.sample_patches(range(lo, hi), noise, x_T)
+            local = self.sample_patches(range(lo, hi), noise, x_T, private_rng=True)
             patches = gather_blocks(local, [b - a for a, b in blocks], dst=0, group=group)
         else:
             rank = 0

@@ -1,10 +1,11 @@
-// extern "C" surface declared in include/drs_b200.h.
+// extern "C" surface declared in include/drs_b200.h (+ the test / instrumentation hooks of include/drs_b200_diag.h).
 #include <string.h>
 
 #include <algorithm>
 #include <memory>
 #include <vector>
 
+#include "../../include/drs_b200_diag.h"
 #include "engine.cuh"
 #include "small_kernels.cuh"
 
@@ -26,8 +27,7 @@ int launch_count(const DrsPlan*);
 int launch_info(const DrsPlan*, int, char*, int, double*, double*, int*, int*);
 int plan_profile(DrsPlan*, const float*, float*, int, float*, cudaStream_t);
 int plan_time_forward(DrsPlan*, const float*, float*, int, float*, cudaStream_t);
-int mma_rate(int, int, int, int, long long*);
-int mma_rate2(int, int, int, int, int, int, int, long long*);
+int sampler_time_hbm_kernels(DrsPlan*, void*, size_t, int, float*, cudaStream_t);
 int debug_bind_and_run(DrsPlan*, const void*, int, int, int, int, void*, int, int, cudaStream_t);
 }  // namespace drs
 
@@ -130,6 +130,15 @@ int drs_plan_time_forward(DrsPlan* p, const float* x_dev, float* eps_dev, int it
   return plan_time_forward(p, x_dev, eps_dev, iters, ms_out2, as_stream(stream));
 }
 
+int drs_sampler_time_hbm_kernels(DrsPlan* p, void* flush_dev, size_t flush_bytes, int iters, float* ms_out2,
+                                 void* stream) {
+  if (!p) {
+    set_error("null plan");
+    return DRS_E_INVALID;
+  }
+  return sampler_time_hbm_kernels(p, flush_dev, flush_bytes, iters, ms_out2, as_stream(stream));
+}
+
 int drs_ddpm_update(float* x_dev, const float* eps_dev, const float* noise_dev_or_null, float c1, float c2, float c3,
                     size_t numel, void* stream) {
   if (!x_dev || !eps_dev) {
@@ -209,14 +218,59 @@ int drs_blend(const float* patches_dev, const int32_t* coords4_host, int n_patch
       set_error("drs_blend: some output pixels are covered by no patch");
       return DRS_E_INVALID;
     }
-    DevMem idx;
-    std::vector<int> both(ys);
-    both.insert(both.end(), xs.begin(), xs.end());
-    DRS_TRY(idx.upload(both.data(), both.size() * sizeof(int)));
-    DRS_CUDA(static_cast<cudaError_t>(launch_blend_gather(patches_dev, idx.as<int>(), static_cast<int>(ys.size()),
-                                                          idx.as<int>() + ys.size(), static_cast<int>(xs.size()),
-                                                          weight_dev, out_dev, wsum_dev, C, H, W, P, do_clamp, st)));
-    DRS_CUDA(cudaStreamSynchronize(st));  // idx is released on return
+    // device tables, cached per calling thread while the window grid stays the same (the aggregation CLI blends one
+    // scene geometry over and over): [ys | xs | pad] then int2 row ranges [H] and int2 quad ranges [W / 4]
+    const bool vec = (P % 4 == 0) && (W % 4 == 0) &&
+                     std::all_of(xs.begin(), xs.end(), [](int x) { return x % 4 == 0; });
+    struct Cache {
+      std::vector<int> key;
+      DevMem tables;
+      int device = -1;
+    };
+    static thread_local Cache cache;
+    std::vector<int> key{H, W, P, vec ? 1 : 0, static_cast<int>(ys.size())};
+    key.insert(key.end(), ys.begin(), ys.end());
+    key.insert(key.end(), xs.begin(), xs.end());
+    int device = 0;
+    DRS_CUDA(cudaGetDevice(&device));
+    const size_t n_starts = (ys.size() + xs.size() + 1) & ~static_cast<size_t>(1);  // keeps the int2 tables aligned
+    if (cache.key != key || cache.device != device || !cache.tables.p) {
+      std::vector<int> host(n_starts, 0);
+      std::copy(ys.begin(), ys.end(), host.begin());
+      std::copy(xs.begin(), xs.end(), host.begin() + ys.size());
+      if (vec) {
+        auto ranges = [&](const std::vector<int>& starts, int extent, int step) {
+          // starts are sorted: the windows covering [p, p + step) form one index interval
+          for (int p0 = 0; p0 < extent; p0 += step) {
+            int lo = 0, hi = 0;
+            while (lo < static_cast<int>(starts.size()) && starts[lo] + P <= p0) ++lo;
+            hi = lo;
+            while (hi < static_cast<int>(starts.size()) && starts[hi] <= p0) ++hi;
+            host.push_back(lo);
+            host.push_back(hi);
+          }
+        };
+        ranges(ys, H, 1);
+        ranges(xs, W, 4);
+      }
+      DRS_CUDA(cudaStreamSynchronize(st));  // a previous blend on this stream may still read the old tables
+      DRS_TRY(cache.tables.upload(host.data(), host.size() * sizeof(int)));
+      cache.key = key;
+      cache.device = device;
+    }
+    const int* d_ys = cache.tables.as<int>();
+    const int* d_xs = d_ys + ys.size();
+    if (vec) {
+      const int2* row_rng = reinterpret_cast<const int2*>(d_ys + n_starts);
+      const int2* col_rng = row_rng + H;
+      DRS_CUDA(static_cast<cudaError_t>(launch_blend_gather4(patches_dev, d_ys, static_cast<int>(ys.size()), d_xs,
+                                                             static_cast<int>(xs.size()), row_rng, col_rng, weight_dev,
+                                                             out_dev, wsum_dev, C, H, W, P, do_clamp, st)));
+    } else {
+      DRS_CUDA(static_cast<cudaError_t>(launch_blend_gather(patches_dev, d_ys, static_cast<int>(ys.size()), d_xs,
+                                                            static_cast<int>(xs.size()), weight_dev, out_dev, wsum_dev,
+                                                            C, H, W, P, do_clamp, st)));
+    }
     return DRS_OK;
   }
   // arbitrary window list: one scatter launch per patch keeps the reference's summation order
@@ -276,18 +330,6 @@ int drs_debug_conv2d(const float* x_dev, const float* w_host, const float* bias_
   DRS_TRY(debug_bind_and_run(p.get(), in_bf.p, gw, gh, H, W, out_bf.p, OH, OW, st));
   DRS_CUDA(static_cast<cudaError_t>(launch_nhwc_bf16_to_nchw(out_bf.p, y_dev, B, Cout, OH, OW, st)));
   DRS_TRY(check_pipeline_error(p.get(), st));
-  return DRS_OK;
-}
-
-int drs_debug_mma_rate(int n, int iters, int unroll4, int ctas_per_sm, long long* out_host) {
-  const int r = mma_rate(n, iters, unroll4, ctas_per_sm, out_host);
-  if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "mma_rate_kernel");
-  return DRS_OK;
-}
-
-int drs_debug_mma_rate2(int n, int nk, int layout, int sbo16, int issuers, int iters, int mode, long long* out_host) {
-  const int r = mma_rate2(n, nk, layout, sbo16, issuers, iters, mode, out_host);
-  if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "mma_rate2_kernel");
   return DRS_OK;
 }
 

@@ -175,26 +175,6 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       }
       int st = 0, sub_first = 0, sub_cnt = 0;
       TL(pno, 0);
-      if (a.l2_prefetch) {
-        // Pull the halo tiles of the pair AFTER this one into L2 now: the A ring only holds about half a pair, so
-        // without this every tile load pays the full HBM latency on the layers whose inputs exceed L2.
-        const int nt0 = tile0 + 2 * tile_step;
-        if (elect_one()) {
-          for (int p = 0; p < 2; ++p) {
-            const int tile = nt0 + p * tile_step;
-            if (tile < a.n_tiles) {
-              const int nb_ = tile / tiles_per_img;
-              const int t2 = tile - nb_ * tiles_per_img;
-              const int ny = (t2 / a.tiles_x) * kTile2H, nx = (t2 % a.tiles_x) * kTile2W;
-              for (int s2 = 0; s2 < a.n_sub_tiles; ++s2) {
-                const SubTile T = prog.st[s2];
-                tma_prefetch_5d(T.src ? &map1 : &map0, T.c, nx + T.dx0, 0, ny + T.dy0, nb_);
-              }
-            }
-          }
-        }
-        __syncwarp();
-      }
       for (int kb = 0; kb < nkb; ++kb) {
         const KB3 K = prog.kb[kb];
         if (K.flags & KB2_FIRST) {
@@ -492,161 +472,6 @@ int launch_conv_gemm2(int epi_kind, const CUtensorMap& map0, const CUtensorMap& 
   }
   if (err != cudaSuccess) return static_cast<int>(err);
   return static_cast<int>(cudaGetLastError());
-}
-
-}  // namespace drs
-
-// ------------------------------------------------------------------------------------------------
-// Micro-benchmark (drs_debug_mma_rate): cycles per tcgen05.mma M=128 x N x K=16 issued back to back by one
-// elected thread on operands resident in shared memory (contents irrelevant).
-// ------------------------------------------------------------------------------------------------
-namespace drs {
-
-struct RateTable { KB3 kb[16]; };
-
-__global__ void __launch_bounds__(128) mma_rate_kernel(int n, int iters, int unroll4, long long* out,
-                                                       const __grid_constant__ RateTable tab) {
-  extern __shared__ uint8_t dyn_smem[];
-  __shared__ __align__(8) uint64_t s_done;
-  __shared__ uint32_t s_tmem_base;
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  const uint32_t dyn_u32 = smem_u32(dyn_smem);
-  uint8_t* const base = dyn_smem + ((1024u - (dyn_u32 & 1023u)) & 1023u);
-  for (int i = threadIdx.x; i < 180 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x3c003c00u;
-  if (threadIdx.x == 0) {
-    mbar_init(&s_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    tmem_alloc(&s_tmem_base, 256);
-    tmem_relinquish();
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = s_tmem_base;
-  if (warp == 1) {
-    // unroll4 bit 0: four MMAs (K slices) per iteration; bits 8..23: A group stride in 16-byte units (default 64 =
-    // 1024 B); bits 24..31: A start offset in 128-byte rows
-    const uint32_t sbo16 = ((unroll4 >> 8) & 0xFFFF) ? ((unroll4 >> 8) & 0xFFFF) : 64u;
-    const uint32_t row0 = (unroll4 >> 24) & 0xFF;
-    const int vary = (unroll4 >> 1) & 1;  // bit 1: walk A over 9 tap offsets and B over 9 weight tiles
-    unroll4 &= 1;
-    const uint32_t a16 = (smem_u32(base) >> 4) + (row0 & 0x7F) * 8u, b16 = smem_u32(base + 32768) >> 4;
-    const uint32_t b16b = smem_u32(base + 24576) >> 4;
-    const uint32_t hi_a = sbo16 | (1u << 14) | (2u << 29);
-    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((static_cast<uint32_t>(n) >> 3) << 17) | (8u << 24);
-    const long long t0 = clock64();
-    if (elect_one()) {
-      uint32_t tap = 0;
-      for (int i = 0; i < iters; ++i) {
-        if (vary && (row0 & 0x80) && (row0 & 0x70)) {
-          // lab: the convolution kernel's issue loop, one feature at a time
-          //   0x10: nk-dependent branches   0x20: accumulate flag from the record   0x40: LAST-flag loop exit
-          const int feat = row0 & 0x70;
-          uint32_t kbi = 0;
-          for (;;) {
-            const KB3 K = tab.kb[kbi];
-            const uint32_t ao = a16 + (K.a_lo & 0xFFFFu), bo = b16b + (K.b_lo & 0xFFFFu);
-            const uint32_t d = tmem + K.col;
-            const uint32_t accf = (feat & 0x20) ? ((K.flags & KB2_INIT) ? 0u : 1u) : 1u;
-            umma_bf16_split(d, (ao & 0x3FFFu) | 0x10000u, K.a_hi, (bo & 0x3FFFu) | 0x10000u, K.b_hi, K.idesc, accf);
-            if (feat & 0x10) {
-              if (K.nk >= 2)
-                umma_bf16_split(d, ((ao + 2u) & 0x3FFFu) | 0x10000u, K.a_hi, ((bo + 2u) & 0x3FFFu) | 0x10000u, K.b_hi, K.idesc, 1u);
-              if (K.nk == 4) {
-                umma_bf16_split(d, ((ao + 4u) & 0x3FFFu) | 0x10000u, K.a_hi, ((bo + 4u) & 0x3FFFu) | 0x10000u, K.b_hi, K.idesc, 1u);
-                umma_bf16_split(d, ((ao + 6u) & 0x3FFFu) | 0x10000u, K.a_hi, ((bo + 6u) & 0x3FFFu) | 0x10000u, K.b_hi, K.idesc, 1u);
-              }
-            } else {
-#pragma unroll
-              for (int k = 1; k < 4; ++k)
-                umma_bf16_split(d, ((ao + 2u * k) & 0x3FFFu) | 0x10000u, K.a_hi, ((bo + 2u * k) & 0x3FFFu) | 0x10000u,
-                                K.b_hi, K.idesc, 1u);
-            }
-            ++kbi;
-            if (feat & 0x40) {
-              if (K.flags & KB2_LAST) break;
-            } else if (kbi == 9u) {
-              break;
-            }
-          }
-        } else if (vary && (row0 & 0x80)) {
-          // descriptors fetched from the kernel-parameter table with a dynamic index, like the convolution kernel
-          const KB3 K = tab.kb[tap];
-          const uint32_t ao = a16 + (K.a_lo & 0xFFFFu), bo = b16b + (K.b_lo & 0xFFFFu);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_split(tmem + K.col, ((ao + 2u * k) & 0x3FFFu) | 0x10000u, K.a_hi, ((bo + 2u * k) & 0x3FFFu) | 0x10000u,
-                            K.b_hi, K.idesc, 1u);
-          tap = (tap == 8u) ? 0u : tap + 1u;
-        } else if (vary) {
-          // same access pattern as the convolution: tap (ky, kx) of a 10-pixel-wide halo tile, its own weight tile
-          const uint32_t ao = a16 + ((tap / 3u) * 10u + (tap % 3u)) * 8u, bo = b16b + tap * (static_cast<uint32_t>(n) * 8u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_split(tmem, ((ao + 2u * k) & 0x3FFFu) | 0x10000u, hi_a, ((bo + 2u * k) & 0x3FFFu) | 0x10000u, hi,
-                            idesc, 1u);
-          tap = (tap == 8u) ? 0u : tap + 1u;
-        } else if (unroll4) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_split(tmem, ((a16 + 2u * k) & 0x3FFFu) | 0x10000u, hi_a, ((b16 + 2u * k) & 0x3FFFu) | 0x10000u, hi,
-                            idesc, 1u);
-        } else {
-          umma_bf16_split(tmem, (a16 & 0x3FFFu) | 0x10000u, hi_a, (b16 & 0x3FFFu) | 0x10000u, hi, idesc, 1u);
-        }
-      }
-      umma_commit(&s_done);
-    }
-    __syncwarp();
-    const long long t1 = clock64();
-    mbar_wait(&s_done, 0, nullptr, 0);
-    const long long t2 = clock64();
-    if (threadIdx.x == 32 && blockIdx.x == 0) {
-      out[0] = t1 - t0;  // issue time
-      out[1] = t2 - t0;  // completion time
-    }
-  } else if (iters < 0) {
-    (void)0;
-  } else if ((n & 1) == 0 && (unroll4 & 0x4)) {
-    // mode bit 2: the other three warps wait on the completion barrier exactly like epilogue warps do
-    mbar_wait(&s_done, 0, nullptr, 0);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 256);
-  }
-}
-
-int mma_rate(int n, int iters, int unroll4, int ctas_per_sm, long long* out_host) {
-  long long* d = nullptr;
-  cudaError_t e = cudaMalloc(&d, 16);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  cudaMemset(d, 0, 16);
-  cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  RateTable tab;
-  memset(&tab, 0, sizeof(tab));
-  for (uint32_t t = 0; t < 9; ++t) {
-    tab.kb[t].a_lo = ((t / 3u) * 10u + (t % 3u)) * 8u;
-    tab.kb[t].b_lo = t * static_cast<uint32_t>(n) * 8u;
-    tab.kb[t].a_hi = 80u | (1u << 14) | (2u << 29);
-    tab.kb[t].b_hi = 64u | (1u << 14) | (2u << 29);
-    tab.kb[t].idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((static_cast<uint32_t>(n) >> 3) << 17) | (8u << 24);
-    tab.kb[t].nk = 4;
-    tab.kb[t].flags = static_cast<uint8_t>((t == 0 ? (KB2_INIT | KB2_FIRST) : 0) | (t == 8 ? KB2_LAST : 0));
-  }
-  mma_rate_kernel<<<sms * ctas_per_sm, 128, 182 * 1024>>>(n, iters, unroll4, d, tab);
-  e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) e = cudaMemcpy(out_host, d, 16, cudaMemcpyDeviceToHost);
-  cudaFree(d);
-  return static_cast<int>(e);
 }
 
 }  // namespace drs

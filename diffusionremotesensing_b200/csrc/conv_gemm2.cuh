@@ -87,7 +87,6 @@ struct Conv2Args {
   int acc_bufs;             // 1 or 2
   int n_sub, nsplit;
   int cg2_half_tile_bytes;  // CTA-pair kernel: bytes of half a (padded) weight tile
-  int l2_prefetch;          // 1: the producer prefetches the next pair's halo tiles into L2
   int solo;                 // 1: both epilogue groups drain every tile, half of the column groups each
   int store_sbc;            // EPI_STD: channels per TMA-store sub-box (0: per-thread global stores, no staging)
   unsigned long long* span_buf;  // debug: device address of the span table (CTA-pair kernel)

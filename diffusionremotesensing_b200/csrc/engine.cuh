@@ -193,6 +193,9 @@ struct DrsPlan {
   float* noise = nullptr;
   float* eps = nullptr;
   bool prepared = false, begun = false;
+  // what the resident time table / coefficient table were built from (drs_sampler_prepare is a no-op on a match)
+  std::vector<float> prep_coef;
+  std::vector<int> prep_uniq, prep_idx;
   cudaGraphExec_t graph_noise = nullptr, graph_last = nullptr;
   cudaStream_t capture_stream = nullptr;
   cudaStream_t side_stream = nullptr;             // attention-gate branch of the decoder stages

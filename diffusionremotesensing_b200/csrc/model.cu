@@ -186,23 +186,7 @@ struct Builder {
       std::set<int> seen;
       int count = 0;
       for (const ConvTerm& t : terms) {
-        int ck = t.C >= 64 ? 64 : t.C;
-        {
-          // experiment knob: DRS_CK32=<comma separated name fragments> halves the channel block (and the A slot) of
-          // the named layers so that twice as many halo tiles are in flight
-          static const char* const ck32 = getenv("DRS_CK32");
-          if (ck32 && ck == 64) {
-            std::string list(ck32);
-            size_t pos = 0;
-            while (pos <= list.size()) {
-              const size_t e = list.find(',', pos);
-              const std::string frag = list.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
-              if (!frag.empty() && g.name.find(frag) != std::string::npos) ck = 32;
-              if (e == std::string::npos) break;
-              pos = e + 1;
-            }
-          }
-        }
+        const int ck = t.C >= 64 ? 64 : t.C;
         if (ck != 16 && ck != 32 && ck != 64) {
           set_error("%s: unsupported source channel count %d", g.name.c_str(), t.C);
           return false;
@@ -332,8 +316,7 @@ struct Builder {
     // Streamed weights travel in units of up to b_unit consecutive K-blocks of one sub-tile (<= 32 KiB): one bulk
     // copy, one full / empty barrier round trip and one tcgen05.commit per unit instead of per K-block.
     const int tile_pad = (max_b + 1023) & ~1023;
-    static const int unit_kib = getenv("DRS_V2_BUNIT_KIB") ? atoi(getenv("DRS_V2_BUNIT_KIB")) : 32;
-    v.b_unit = std::max(1, std::min(4, (unit_kib * 1024) / tile_pad));
+    v.b_unit = std::max(1, std::min(4, (32 * 1024) / tile_pad));
     v.b_stage_bytes = v.resident ? tile_pad : v.b_unit * tile_pad;
     v.w_split_bytes = static_cast<uint32_t>(w_image);
     while (m->wblob.size() % 1024) m->wblob.push_back(0);

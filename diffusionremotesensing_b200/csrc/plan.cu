@@ -228,9 +228,6 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   static const bool no_solo = (getenv("DRS_V2_NO_SOLO") != nullptr);
   a.solo = (!no_solo && g.epi_kind == EPI_STD && a.acc_bufs == 1 && g.n_groups >= 2 && g.n_groups % 2 == 0) ? 1 : 0;
   a.err = p->d_err;
-  // L2 prefetch of the next pair's tiles (DRS_V2_L2_PREFETCH=1): measured +4 % step time at cfg 2, off by default
-  static const int l2pf = getenv("DRS_V2_L2_PREFETCH") ? atoi(getenv("DRS_V2_L2_PREFETCH")) : 0;
-  a.l2_prefetch = l2pf;
   static const int timeline = getenv("DRS_V2_TIMELINE") ? atoi(getenv("DRS_V2_TIMELINE")) : 0;
   // bit 0: record stamps, bit 1: skip the epilogue body (timing experiments only); DRS_V2_TIMELINE_LAYER restricts
   // the recording to launches whose name contains the given substring
@@ -242,23 +239,19 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   // (sub-tile, tile-of-pair) and every slot is released after its own taps, so two slots per sub-tile in flight plus
   // two of prefetch keep both issuers fed.
   const int spt = a.n_sub_tiles;
-  static const int b_stage_knob = getenv("DRS_V2_BSTAGES") ? atoi(getenv("DRS_V2_BSTAGES")) : 3;
-  a.b_stages = a.resident ? 1 : std::min(std::min(b_stage_knob, kMaxBStages), v.nkb);
+  a.b_stages = a.resident ? 1 : std::min(3, v.nkb);
   const int b_bytes = a.resident ? static_cast<int>(v.w_split_bytes) : a.b_stages * v.b_stage_bytes;
   const int want_slots = std::min(kMaxASlots, std::max(4, 2 * spt + 2));
   // Staged TMA-store epilogue (EPI_STD, bf16 NHWC output whose tiles never straddle two images): 4 KiB per
   // epilogue warp, taken when at least four A slots still fit.
   static const bool no_stage = (getenv("DRS_V2_NO_TMA_STORE") != nullptr);
-  // DRS_V2_STAGE_MIN_N: outputs narrower than this are written with per-thread 256-bit stores instead. Measured at
-  // cfg 2: staging everything (16) 0.879 ms/step, >= 64 channels only 0.899, >= 128 only 0.902.
-  static const int stage_min_n = getenv("DRS_V2_STAGE_MIN_N") ? atoi(getenv("DRS_V2_STAGE_MIN_N")) : 16;
-  const bool can_stage = !no_stage && g.epi_kind == EPI_STD && (g.n_sub % 16) == 0 && g.OC >= stage_min_n &&
+  // Every width is staged (measured at cfg 2: staging everything 0.879 ms/step, >= 64 channels only 0.899).
+  const bool can_stage = !no_stage && g.epi_kind == EPI_STD && (g.n_sub % 16) == 0 &&
                          (g.oscale == 1 || (a.epi.OW % 2 == 0 && a.epi.OH % 2 == 0));
   int stage_bytes = 0;
   // Each CTA already runs two MMA issuers and two epilogue groups; a second co-resident CTA is taken when TMEM and
   // shared memory allow it.
-  static const int max_ctas = getenv("DRS_V2_MAX_CTAS") ? atoi(getenv("DRS_V2_MAX_CTAS")) : 2;
-  int ctas = std::min(512 / alloc, max_ctas);
+  int ctas = std::min(512 / alloc, 2);
   int slots = 0;
   for (; ctas >= 1; --ctas) {
     const int budget = (227 * 1024) / ctas - 14 * 1024 - b_bytes;
@@ -270,8 +263,6 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
     slots = std::min(want_slots, (budget - stage_bytes) / v.a_slot_bytes) & ~1;
     if (slots >= 4 || ctas == 1) break;
   }
-  static const int force_slots = getenv("DRS_V2_SLOTS") ? atoi(getenv("DRS_V2_SLOTS")) : 0;
-  if (force_slots > 0 && force_slots <= slots) slots = force_slots & ~1;  // debugging knob
   if (slots < 2) return DRS_OK;  // does not fit: stay on the first-generation kernel
   a.a_slots = slots;
   a.store_sbc = 0;
@@ -279,8 +270,7 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
     // One sub-box per tile (N <= 64, one column group) can use the whole 4 KiB staging area; with several sub-boxes
     // per tile a single buffer would make every sub-box wait for the TMA unit to read the previous one, so the area
     // is split into two 32-channel (or four 16-channel) buffers that rotate.
-    static const int sbc_multi = getenv("DRS_V2_SBC_MULTI") ? atoi(getenv("DRS_V2_SBC_MULTI")) : 64;
-    a.store_sbc = (g.n_sub * g.n_groups > 64) ? std::min(sbc_multi, g.n_sub) : std::min(64, g.n_sub);
+    a.store_sbc = std::min(64, g.n_sub);
     const int r = make_map(&L->map_out, a.epi.out, p->nb, a.epi.OH, a.epi.OW, a.epi.OC, g.oscale == 2, a.store_sbc,
                            kTile2W, 4, 1, 1);
     if (r != DRS_OK) return r;
@@ -350,12 +340,10 @@ static int bind_launch_cg2(DrsPlan* p, Launch* L) {
   a.resident = (half_image + 4 * v.a_slot_bytes <= budget) ? 1 : 0;
   if (!cg2_wanted(g.name, v.resident, a.resident != 0, v.nkb)) return DRS_OK;
   // half-size tiles: twice as many K-blocks per ring stage for the same bytes (fewer full / empty round trips)
-  static const int cg2_unit_kib = getenv("DRS_CG2_BUNIT_KIB") ? atoi(getenv("DRS_CG2_BUNIT_KIB")) : 32;
-  const int unit_c = std::max(1, std::min(8, (cg2_unit_kib * 1024) / half));
+  const int unit_c = std::max(1, std::min(8, (32 * 1024) / half));
   a.b_unit = unit_c;
   a.b_stage_bytes = unit_c * half;
-  static const int cg2_stages = getenv("DRS_CG2_BSTAGES") ? atoi(getenv("DRS_CG2_BSTAGES")) : 3;
-  a.b_stages = a.resident ? 1 : std::min(std::min(cg2_stages, kMaxBStages), (v.nkb + unit_c - 1) / unit_c);
+  a.b_stages = a.resident ? 1 : std::min(3, (v.nkb + unit_c - 1) / unit_c);
   const int b_bytes = a.resident ? half_image : a.b_stages * a.b_stage_bytes;
   int stage_bytes = a.store_sbc ? kStageBytes : 0;
   if (stage_bytes && (((budget - b_bytes - stage_bytes) / v.a_slot_bytes) & ~1) < 4) {
@@ -394,8 +382,8 @@ static int bind_launch_cg2(DrsPlan* p, Launch* L) {
   }
   // one CTA pair per TPC: pad the request so that no second CTA fits beside it (two co-resident pairs interleave
   // their TMEM pair allocations)
-  static const int min_smem = getenv("DRS_CG2_MIN_SMEM_KIB") ? atoi(getenv("DRS_CG2_MIN_SMEM_KIB")) * 1024 : 116 * 1024;
-  if (L->smem_c < static_cast<size_t>(min_smem)) L->smem_c = static_cast<size_t>(min_smem);
+  const size_t min_smem = 116 * 1024;
+  if (L->smem_c < min_smem) L->smem_c = min_smem;
   const int max_clusters = conv_gemm2c_max_clusters(g.flags, L->smem_c);
   if (max_clusters < g.nsplit) return DRS_OK;
   const int n_units = a.n_tiles / 2;
@@ -517,7 +505,7 @@ int plan_create(DrsModel* m, int nb, int nx, int ncond, int S, int mag, DrsPlan*
       const ActTensor& s0w = p->acts.at(w.src_name[0]);
       const int gh = w.src_stride2[0] ? s0w.H / 2 : s0w.H, gw = w.src_stride2[0] ? s0w.W / 2 : s0w.W;
       const long tiles = static_cast<long>(p->nb) * ((gh + kTile2H - 1) / kTile2H) * ((gw + kTile2W - 1) / kTile2W);
-      static const int narrow_below = getenv("DRS_NARROW_BELOW") ? atoi(getenv("DRS_NARROW_BELOW")) : 74;
+      const int narrow_below = 74;  // half of the SMs (thresholds 148 / 300 lose 5 / 13 % at cfg 2)
       const long ctas_wide = ((tiles + 1) / 2) * w.nsplit;
       if (li < m->alt.size() && m->alt[li] >= 0 && gh >= kTile2H && gw >= kTile2W && ctas_wide < narrow_below)
         gi = static_cast<size_t>(m->alt[li]);
@@ -851,6 +839,27 @@ int sampler_prepare(DrsPlan* p, int noise_steps, const float* c1, const float* c
   } else {
     uniq.push_back(-1);
   }
+  std::vector<float> hc(static_cast<size_t>(noise_steps) * 4);
+  for (int i = 0; i < noise_steps; ++i) {
+    hc[4 * i + 0] = c1[i];
+    hc[4 * i + 1] = c2[i];
+    hc[4 * i + 2] = c3[i];
+    hc[4 * i + 3] = 0.f;
+  }
+  // Repeated sample() calls (aggregation sampling runs one per patch batch): when the schedule, the label set and
+  // the batch's label indices are the ones the resident tables were built from, nothing is rebuilt, the stream is
+  // not synchronised and both captured graphs stay valid. cfg_scale is a kernel argument inside the graphs.
+  if (p->prepared && p->noise_steps == noise_steps && p->prep_coef == hc && p->prep_uniq == uniq &&
+      p->prep_idx == idx) {
+    if (p->cfg_scale != cfg_scale) {
+      DRS_CUDA(cudaStreamSynchronize(st));
+      drop_graphs(p);
+      p->cfg_scale = cfg_scale;
+    }
+    p->begun = false;
+    return DRS_OK;
+  }
+  p->prepared = false;
   p->n_uniq = static_cast<int>(uniq.size());
   p->noise_steps = noise_steps;
   p->cfg_scale = cfg_scale;
@@ -863,13 +872,6 @@ int sampler_prepare(DrsPlan* p, int noise_steps, const float* c1, const float* c
     rebind_table(p);
   }
   DevMem tv, lb;
-  std::vector<float> hc(static_cast<size_t>(noise_steps) * 4);
-  for (int i = 0; i < noise_steps; ++i) {
-    hc[4 * i + 0] = c1[i];
-    hc[4 * i + 1] = c2[i];
-    hc[4 * i + 2] = c3[i];
-    hc[4 * i + 3] = 0.f;
-  }
   DRS_TRY(p->coef.upload(hc.data(), hc.size() * sizeof(float)));
   p->d_coef = p->coef.as<float>();
   DRS_CUDA(cudaMemcpy(p->d_uniq, idx.data(), p->nb * sizeof(int), cudaMemcpyHostToDevice));
@@ -891,6 +893,9 @@ int sampler_prepare(DrsPlan* p, int noise_steps, const float* c1, const float* c
                             m->label_emb >= 0 ? lb.as<int>() : nullptr, R, st));
     DRS_CUDA(cudaStreamSynchronize(st));
   }
+  p->prep_coef = std::move(hc);
+  p->prep_uniq = uniq;
+  p->prep_idx = idx;
   p->prepared = true;
   p->begun = false;
   return DRS_OK;
@@ -968,6 +973,53 @@ int sampler_step(DrsPlan* p, int use_graph, cudaStream_t st) {
   }
   p->cur_step -= 1;
   return DRS_OK;
+}
+
+// Event-timed durations of the two CUDA-core kernels of a reverse step, each launch on a cold L2 (the caller's flush
+// buffer, larger than L2, is overwritten before every timed launch): ms_out[0] = conv0, ms_out[1] = posterior update
+// with its bookkeeping tail. The sampler's step index is restored afterwards.
+int sampler_time_hbm_kernels(DrsPlan* p, void* flush_dev, size_t flush_bytes, int iters, float* ms_out,
+                             cudaStream_t st) {
+  if (!p->begun || !ms_out || iters < 1 || iters >= p->cur_step) {
+    set_error("drs_sampler_time_hbm_kernels: needs a begun sampler with more than `iters` steps left");
+    return DRS_E_STATE;
+  }
+  const DrsModel* m = p->m;
+  const ActTensor& h0 = p->acts.at("h0");
+  const size_t numel = static_cast<size_t>(p->nx) * m->desc.out_channels * p->S * p->S;
+  const int cfg = (p->nb == 2 * p->nx) ? 1 : 0;
+  cudaEvent_t ev[4];
+  for (auto& e : ev) DRS_CUDA(cudaEventCreate(&e));
+  double acc[2] = {0.0, 0.0};
+  int rc = DRS_OK;
+  for (int it = 0; it < iters && rc == DRS_OK; ++it) {
+    if (flush_dev) cudaMemsetAsync(flush_dev, it & 0xFF, flush_bytes, st);
+    cudaEventRecord(ev[0], st);
+    int r = launch_conv0(p->x, m->fblob.data() + m->conv0.w, m->fblob.data() + m->conv0.b,
+                         m->has_cond ? p->cond_feat.as<float>() : nullptr, p->workspace.as<uint8_t>() + h0.offset,
+                         p->nb, p->nx, m->has_cond ? p->ncond : 1, m->desc.x_channels, p->S, st);
+    cudaEventRecord(ev[1], st);
+    if (r != 0) rc = cuda_fail(static_cast<cudaError_t>(r), "conv0 (timing)");
+    if (flush_dev) cudaMemsetAsync(flush_dev, (it + 1) & 0xFF, flush_bytes, st);
+    cudaEventRecord(ev[2], st);
+    r = launch_ddpm_update(p->x, p->eps, p->noise, p->d_coef, p->d_step, numel, cfg, p->cfg_scale, p->d_trow, p->nb,
+                           p->n_uniq, p->d_step + 1, st);
+    cudaEventRecord(ev[3], st);
+    if (r != 0) rc = cuda_fail(static_cast<cudaError_t>(r), "ddpm_update (timing)");
+    const cudaError_t se = cudaStreamSynchronize(st);
+    if (se != cudaSuccess) rc = cuda_fail(se, "cudaStreamSynchronize(time_hbm_kernels)");
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, ev[0], ev[1]);
+    cudaEventElapsedTime(&b, ev[2], ev[3]);
+    acc[0] += a;
+    acc[1] += b;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  ms_out[0] = static_cast<float>(acc[0] / iters);
+  ms_out[1] = static_cast<float>(acc[1] / iters);
+  DRS_CUDA(static_cast<cudaError_t>(
+      launch_set_rows(p->d_trow, p->d_uniq, p->nb, p->d_step, p->cur_step, p->n_uniq, st)));
+  return rc;
 }
 
 // drs_debug_conv2d: binds gemms[0] of a single-layer model to caller buffers and runs it once.

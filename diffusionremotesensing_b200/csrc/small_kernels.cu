@@ -370,38 +370,60 @@ __device__ __forceinline__ float lerp_aten(float u, float c, float w) {
 // trow / counter (optional): sampler bookkeeping folded into this launch. Every block reads *step before it does
 // anything else and bumps `counter` when it is done, so the block that brings the count to gridDim.x knows that nobody
 // still needs the old value: it decrements the step index and the time-table rows and re-arms the counter.
-__global__ void ddpm_update_kernel(float* __restrict__ x, const float* __restrict__ eps,
-                                   const float* __restrict__ noise, const float* __restrict__ coef, int* step,
-                                   size_t n4, int cfg, float cfg_scale, int* trow, int n_rows, int row_dec,
-                                   int* counter) {
+// Each thread owns kUpdU float4 quads a block-stride apart and issues all of its loads before the first use, so one
+// round trip to HBM covers the whole kernel (the r1 form ran four dependent round trips per block: step, coefficient,
+// data, fence + atomic). `step` and the coefficient row were written at least one whole launch earlier, so they are
+// read BEFORE griddepcontrol.wait and overlap the tail of the preceding convolution.
+constexpr int kUpdU = 4;
+template <bool CFG>
+__global__ void __launch_bounds__(256, CFG ? 3 : 4)
+ddpm_update_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
+                   const float* __restrict__ coef, int* step, size_t n4, float cfg_scale, int* trow,
+                   int n_rows, int row_dec, int* counter) {
+  constexpr bool cfg = CFG;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   const float4 cf = __ldg(reinterpret_cast<const float4*>(coef) + *reinterpret_cast<volatile int*>(step));
-  const bool has_z = (noise != nullptr) && (cf.z != 0.f || true);
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 xv = reinterpret_cast<float4*>(x)[i];
-    float4 ev = __ldg(reinterpret_cast<const float4*>(eps) + i);
-    if (cfg) {
-      const float4 uv = __ldg(reinterpret_cast<const float4*>(eps) + n4 + i);
-      ev.x = lerp_aten(uv.x, ev.x, cfg_scale);
-      ev.y = lerp_aten(uv.y, ev.y, cfg_scale);
-      ev.z = lerp_aten(uv.z, ev.z, cfg_scale);
-      ev.w = lerp_aten(uv.w, ev.w, cfg_scale);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const bool has_z = (noise != nullptr);
+  const size_t base = static_cast<size_t>(blockIdx.x) * (256 * kUpdU) + threadIdx.x;
+  float4 xv[kUpdU], ev[kUpdU], uv[CFG ? kUpdU : 1], zv[kUpdU];
+#pragma unroll
+  for (int u = 0; u < kUpdU; ++u) {
+    const size_t i = base + static_cast<size_t>(u) * 256;
+    xv[u] = ev[u] = zv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cfg) uv[CFG ? u : 0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+      xv[u] = reinterpret_cast<const float4*>(x)[i];
+      ev[u] = __ldcs(reinterpret_cast<const float4*>(eps) + i);
+      if (cfg) uv[CFG ? u : 0] = __ldcs(reinterpret_cast<const float4*>(eps) + n4 + i);
+      if (has_z) zv[u] = __ldcs(reinterpret_cast<const float4*>(noise) + i);
     }
-    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_z) zv = __ldg(reinterpret_cast<const float4*>(noise) + i);
-    xv.x = ddpm_one(xv.x, ev.x, zv.x, cf.x, cf.y, cf.z, has_z);
-    xv.y = ddpm_one(xv.y, ev.y, zv.y, cf.x, cf.y, cf.z, has_z);
-    xv.z = ddpm_one(xv.z, ev.z, zv.z, cf.x, cf.y, cf.z, has_z);
-    xv.w = ddpm_one(xv.w, ev.w, zv.w, cf.x, cf.y, cf.z, has_z);
-    reinterpret_cast<float4*>(x)[i] = xv;
+  }
+#pragma unroll
+  for (int u = 0; u < kUpdU; ++u) {
+    const size_t i = base + static_cast<size_t>(u) * 256;
+    if (i >= n4) continue;
+    float4 e4 = ev[u];
+    if (cfg) {
+      const float4 u4 = uv[CFG ? u : 0];
+      e4.x = lerp_aten(u4.x, e4.x, cfg_scale);
+      e4.y = lerp_aten(u4.y, e4.y, cfg_scale);
+      e4.z = lerp_aten(u4.z, e4.z, cfg_scale);
+      e4.w = lerp_aten(u4.w, e4.w, cfg_scale);
+    }
+    float4 o;
+    o.x = ddpm_one(xv[u].x, e4.x, zv[u].x, cf.x, cf.y, cf.z, has_z);
+    o.y = ddpm_one(xv[u].y, e4.y, zv[u].y, cf.x, cf.y, cf.z, has_z);
+    o.z = ddpm_one(xv[u].z, e4.z, zv[u].z, cf.x, cf.y, cf.z, has_z);
+    o.w = ddpm_one(xv[u].w, e4.w, zv[u].w, cf.x, cf.y, cf.z, has_z);
+    reinterpret_cast<float4*>(x)[i] = o;
   }
   if (trow) {
+    // No fence: the only cross-block hazard is a block still reading the OLD *step after the last block wrote the new
+    // one, and every block's read completed (its value fed the coefficient load consumed above) before its atomic.
     __shared__ int s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-      __threadfence();
       const int done = atomicAdd(counter, 1);
       s_last = (done == static_cast<int>(gridDim.x) - 1) ? 1 : 0;
     }
@@ -437,10 +459,12 @@ int launch_ddpm_update(float* x, const float* eps, const float* noise, const flo
                        int cfg, float cfg_scale, int* trow, int n_rows, int row_dec, int* counter, cudaStream_t s) {
   if (numel % 4) return static_cast<int>(cudaErrorInvalidValue);
   const size_t n4 = numel / 4;
-  int blocks = cdiv(static_cast<long long>(n4), 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  const cudaError_t e = launch_pdl(ddpm_update_kernel, dim3(blocks), dim3(256), s, x, eps, noise, coef, step, n4, cfg,
-                                   cfg_scale, trow, n_rows, row_dec, counter);
+  const int blocks = cdiv(static_cast<long long>(n4), 256 * kUpdU);
+  const cudaError_t e =
+      cfg ? launch_pdl(ddpm_update_kernel<true>, dim3(blocks), dim3(256), s, x, eps, noise, coef, step, n4, cfg_scale,
+                       trow, n_rows, row_dec, counter)
+          : launch_pdl(ddpm_update_kernel<false>, dim3(blocks), dim3(256), s, x, eps, noise, coef, step, n4, cfg_scale,
+                       trow, n_rows, row_dec, counter);
   if (e != cudaSuccess) return static_cast<int>(e);
   return static_cast<int>(cudaGetLastError());
 }
@@ -529,6 +553,86 @@ int launch_blend_gather(const float* patches, const int* ys, int ny, const int* 
   if (C > 4) return static_cast<int>(cudaErrorInvalidValue);
   dim3 grid(cdiv(W, 256), H);
   blend_gather_kernel<<<grid, 256, 0, s>>>(patches, ys, ny, xs, nx, weight, out, wsum_out, C, H, W, P, do_clamp);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// Vector form (window starts, P and W multiples of 4): one thread = four consecutive output pixels of one row, every
+// access a 128-bit one (a warp reads 512 contiguous bytes of each patch row it touches). The windows covering a row /
+// a pixel quad come from two small range tables built on the host ((first, last + 1) indices into the sorted start
+// lists), so nothing is scanned. Patches are visited in row-major patch order and every pixel is accumulated with a
+// separately rounded multiply and add, exactly like the scalar kernel and the reference's `+=` sequence.
+template <int C>
+__global__ void __launch_bounds__(256)
+blend_gather4_kernel(const float* __restrict__ patches, const int* __restrict__ ys, const int* __restrict__ xs, int nx,
+                     const int2* __restrict__ row_rng, const int2* __restrict__ col_rng,
+                     const float* __restrict__ weight, float* __restrict__ out, float* __restrict__ wsum_out, int H,
+                     int W, int P, int do_clamp) {
+  const int X4 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y;
+  if (4 * X4 >= W) return;
+  const int X = 4 * X4;
+  const int2 ry = __ldg(row_rng + Y);
+  const int2 cx = __ldg(col_rng + X4);
+  float4 acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 cnt = make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t pp = static_cast<size_t>(P) * P;
+  for (int iy = ry.x; iy < ry.y; ++iy) {
+    const int ly = Y - __ldg(ys + iy);
+    for (int ix = cx.x; ix < cx.y; ++ix) {
+      const int lx = X - __ldg(xs + ix);
+      const size_t o = static_cast<size_t>(ly) * P + lx;
+      const float4 w = __ldg(reinterpret_cast<const float4*>(weight + o));
+      const float* pb = patches + static_cast<size_t>(iy * nx + ix) * C * pp + o;
+      float4 v[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c] = __ldcs(reinterpret_cast<const float4*>(pb + c * pp));
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        acc[c].x = __fadd_rn(acc[c].x, __fmul_rn(v[c].x, w.x));
+        acc[c].y = __fadd_rn(acc[c].y, __fmul_rn(v[c].y, w.y));
+        acc[c].z = __fadd_rn(acc[c].z, __fmul_rn(v[c].z, w.z));
+        acc[c].w = __fadd_rn(acc[c].w, __fmul_rn(v[c].w, w.w));
+      }
+      cnt.x = __fadd_rn(cnt.x, w.x);
+      cnt.y = __fadd_rn(cnt.y, w.y);
+      cnt.z = __fadd_rn(cnt.z, w.z);
+      cnt.w = __fadd_rn(cnt.w, w.w);
+    }
+  }
+  const size_t po = static_cast<size_t>(Y) * W + X;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float4 r;
+    r.x = __fdiv_rn(acc[c].x, cnt.x);
+    r.y = __fdiv_rn(acc[c].y, cnt.y);
+    r.z = __fdiv_rn(acc[c].z, cnt.z);
+    r.w = __fdiv_rn(acc[c].w, cnt.w);
+    if (do_clamp) {
+      r.x = fminf(fmaxf(r.x, 0.f), 1.f);
+      r.y = fminf(fmaxf(r.y, 0.f), 1.f);
+      r.z = fminf(fmaxf(r.z, 0.f), 1.f);
+      r.w = fminf(fmaxf(r.w, 0.f), 1.f);
+    }
+    __stcs(reinterpret_cast<float4*>(out + static_cast<size_t>(c) * H * W + po), r);
+  }
+  if (wsum_out) __stcs(reinterpret_cast<float4*>(wsum_out + po), cnt);
+}
+
+// tables: [ny + nx] window starts, then int2 row_rng[H], int2 col_rng[W / 4] (device, 8-byte aligned ranges)
+int launch_blend_gather4(const float* patches, const int* ys, int ny, const int* xs, int nx, const int2* row_rng,
+                         const int2* col_rng, const float* weight, float* out, float* wsum_out, int C, int H, int W,
+                         int P, int do_clamp, cudaStream_t s) {
+  (void)ny;
+  dim3 grid(cdiv(W / 4, 256), H);
+  switch (C) {
+    case 1: blend_gather4_kernel<1><<<grid, 256, 0, s>>>(patches, ys, xs, nx, row_rng, col_rng, weight, out, wsum_out, H, W, P, do_clamp); break;
+    case 2: blend_gather4_kernel<2><<<grid, 256, 0, s>>>(patches, ys, xs, nx, row_rng, col_rng, weight, out, wsum_out, H, W, P, do_clamp); break;
+    case 3: blend_gather4_kernel<3><<<grid, 256, 0, s>>>(patches, ys, xs, nx, row_rng, col_rng, weight, out, wsum_out, H, W, P, do_clamp); break;
+    case 4: blend_gather4_kernel<4><<<grid, 256, 0, s>>>(patches, ys, xs, nx, row_rng, col_rng, weight, out, wsum_out, H, W, P, do_clamp); break;
+    default: return static_cast<int>(cudaErrorInvalidValue);
+  }
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -47,6 +47,11 @@ int launch_set_rows(int* trow, const int* base_host_like_dev, int n, int* step, 
 //   out fp32 [C, H, W] = clamp(sum_p patch*w / sum_p w, 0, 1); wsum_out optional [H, W].
 int launch_blend_gather(const float* patches, const int* ys, int ny, const int* xs, int nx, const float* weight,
                         float* out, float* wsum_out, int C, int H, int W, int P, int do_clamp, cudaStream_t s);
+// Vector form of the same (window starts, P and W multiples of 4): 128-bit accesses, four pixels per thread, window
+// ranges per output row / pixel quad from host-built tables instead of a scan.
+int launch_blend_gather4(const float* patches, const int* ys, int ny, const int* xs, int nx, const int2* row_rng,
+                         const int2* col_rng, const float* weight, float* out, float* wsum_out, int C, int H, int W,
+                         int P, int do_clamp, cudaStream_t s);
 // Scatter form used for arbitrary window lists: one launch per patch keeps the reference's summation order.
 int launch_blend_accumulate(const float* patch, const float* weight, float* acc, float* wsum, int C, int H, int W,
                             int P, int y0, int x0, cudaStream_t s);

@@ -133,7 +133,7 @@ class _DiffusionBase:
                          labels: Optional[torch.Tensor], cfg: bool, cfg_scale: float,
                          noise: Optional[Callable[[int], torch.Tensor]], frames: Optional[List[torch.Tensor]],
                          use_graph: bool = True, start_step: Optional[int] = None,
-                         n_steps: Optional[int] = None) -> torch.Tensor:
+                         n_steps: Optional[int] = None, generator: Optional[torch.Generator] = None) -> torch.Tensor:
         """x: [nx, C, S, S] fp32 on the device (updated in place and returned); cond: [1 or nx, Cc, h, w] or None;
         labels: int32 [nx] or None; cfg: run the conditional and unconditional passes as one batch of 2 nx."""
         dev = x.device
@@ -156,9 +156,12 @@ class _DiffusionBase:
             if cfg:
                 lab = torch.cat([lab, torch.full((nx,), -1, dtype=torch.int32)])
             lab_host = lab.contiguous()
-        out_c = model._desc().out_channels
-        eps = torch.empty((nb, out_c, S, S), device=dev, dtype=torch.float32)
-        zbuf = torch.empty_like(x)
+        # the sampler works in buffers owned by the plan (same addresses on every call -> captured graphs stay valid)
+        bufs = model.sampler_buffers(nb, nx, ncond, S, mag)
+        if tuple(bufs["x"].shape) != tuple(x.shape):
+            raise ValueError("state has shape %s, the model expects %s" % (tuple(x.shape), tuple(bufs["x"].shape)))
+        xs, zbuf, eps = bufs["x"], bufs["z"], bufs["eps"]
+        xs.copy_(x)
         first = self.noise_steps - 1 if start_step is None else start_step
         last = 1 if n_steps is None else max(1, first - n_steps + 1)
         with torch.cuda.device(dev):
@@ -166,17 +169,18 @@ class _DiffusionBase:
                 N.check(lib.drs_cond_encode(plan, N.ptr(cond), st))
             N.check(lib.drs_sampler_prepare(plan, self.noise_steps, N.ptr(c1), N.ptr(c2), N.ptr(c3), N.ptr(lab_host),
                                             float(cfg_scale), st))
-            N.check(lib.drs_sampler_begin(plan, N.ptr(x), N.ptr(zbuf), N.ptr(eps), first, st))
+            N.check(lib.drs_sampler_begin(plan, N.ptr(xs), N.ptr(zbuf), N.ptr(eps), first, st))
             for i in range(first, last - 1, -1):
                 if i > 1:
                     if noise is None:
-                        zbuf.normal_()          # same generator call sequence as torch.randn_like(x)
+                        zbuf.normal_(generator=generator)  # same generator call sequence as torch.randn_like(x)
                     else:
                         zbuf.copy_(noise(i).to(dev, torch.float32))
                 N.check(lib.drs_sampler_step(plan, 1 if use_graph else 0, st))
                 if frames is not None:
-                    frames.append(x.clone())
+                    frames.append(xs.clone())
             N.check(lib.drs_plan_check(plan, st))
+        x.copy_(xs)
         return x
 
     def _finish(self, model, frames, generate_video):
@@ -202,9 +206,10 @@ class _DiffusionBase:
             writer.write(np.ascontiguousarray(img[:, :, ::-1]))
         writer.release()
 
-    def _start_state(self, n, channels, x_T, dev):
+    def _start_state(self, n, channels, x_T, dev, cpu_generator=None):
         if x_T is None:
-            x = torch.randn((n, channels, self.image_size, self.image_size))  # CPU default generator, like the reference
+            # CPU default generator, like the reference (a private one only for sharded aggregation sampling)
+            x = torch.randn((n, channels, self.image_size, self.image_size), generator=cpu_generator)
         else:
             x = x_T
             if tuple(x.shape) != (n, channels, self.image_size, self.image_size):
@@ -224,33 +229,40 @@ class Diffusion(_DiffusionBase):
                           model_name, multiple_gpus, ema_smoothing)
 
     def sample(self, n, model, lr_img, input_channels=3, generate_video=False, *, x_T=None, noise=None,
-               use_graph=True):
-        """n stochastic super-resolutions of ONE low-resolution image [C, h, w] -> [n, C, S, S] fp32, unclamped."""
+               use_graph=True, n_steps=None):
+        """n stochastic super-resolutions of ONE low-resolution image [C, h, w] -> [n, C, S, S] fp32, unclamped.
+        n_steps (keyword extension, tests / benchmarks): stop after the first n_steps reverse steps of the chain."""
         dev = self._native_device()
         lr = lr_img.to(dev).unsqueeze(0)
-        return self._sample_conditioned(n, model, lr, input_channels, generate_video, x_T, noise, use_graph)
+        return self._sample_conditioned(n, model, lr, input_channels, generate_video, x_T, noise, use_graph,
+                                        n_steps=n_steps)
 
-    def sample_batched(self, model, lr_imgs, input_channels=3, *, x_T=None, noise=None, use_graph=True):
+    def sample_batched(self, model, lr_imgs, input_channels=3, *, x_T=None, noise=None, use_graph=True,
+                       generator=None, cpu_generator=None, n_steps=None):
         """One super-resolution per low-resolution image of a batch [n, C, h, w] (used by aggregation sampling; the
-        reference can only express this as n sequential sample(1, ...) calls, Aggregation_Sampling.py:94-95)."""
+        reference can only express this as n sequential sample(1, ...) calls, Aggregation_Sampling.py:94-95).
+        generator / cpu_generator: optional private torch.Generators for the per-step device noise and for x_T
+        (default: the global ones, like the reference)."""
         dev = self._native_device()
         return self._sample_conditioned(lr_imgs.shape[0], model, lr_imgs.to(dev), input_channels, False, x_T, noise,
-                                        use_graph)
+                                        use_graph, generator, cpu_generator, n_steps)
 
-    def _sample_conditioned(self, n, model, lr, input_channels, generate_video, x_T, noise, use_graph):
+    def _sample_conditioned(self, n, model, lr, input_channels, generate_video, x_T, noise, use_graph,
+                            generator=None, cpu_generator=None, n_steps=None):
         dev = self._native_device()
         frames = [] if generate_video else None
         model.eval()
         with torch.no_grad():
             if self.Degradation_type.lower() not in ("downblur", "bsrgan", "downblurnoise"):
                 raise ValueError("The degradation type must be either BSRGAN or DownBlur")
-            x = self._start_state(n, input_channels, x_T, dev)
+            x = self._start_state(n, input_channels, x_T, dev, cpu_generator)
             mag = int(self.magnification_factor)
             if lr.shape[-1] * mag != self.image_size or lr.shape[-2] * mag != self.image_size:
                 raise ValueError("lr_img size %s times magnification %d must equal image_size %d"
                                  % (tuple(lr.shape[-2:]), mag, self.image_size))
             lr = lr.to(torch.float32).contiguous()
-            x = self._reverse_process(model, x, lr, mag, None, False, 0.0, noise, frames, use_graph)
+            x = self._reverse_process(model, x, lr, mag, None, False, 0.0, noise, frames, use_graph,
+                                      n_steps=n_steps, generator=generator)
         self._finish(model, frames, generate_video)
         return x
 
@@ -265,7 +277,7 @@ class Diffusion_SAR_TO_NDVI(_DiffusionBase):
                           model_name, multiple_gpus, ema_smoothing)
 
     def sample(self, n, model, SAR_img, NDVI_channels=1, generate_video=False, *, x_T=None, noise=None,
-               use_graph=True):
+               use_graph=True, n_steps=None):
         dev = self._native_device()
         sar = SAR_img.to(dev).unsqueeze(0).to(torch.float32).contiguous()
         frames = [] if generate_video else None
@@ -274,7 +286,7 @@ class Diffusion_SAR_TO_NDVI(_DiffusionBase):
             x = self._start_state(n, NDVI_channels, x_T, dev)
             if sar.shape[-1] != self.image_size or sar.shape[-2] != self.image_size:
                 raise ValueError("SAR_img must be [C, image_size, image_size]")
-            x = self._reverse_process(model, x, sar, 1, None, False, 0.0, noise, frames, use_graph)
+            x = self._reverse_process(model, x, sar, 1, None, False, 0.0, noise, frames, use_graph, n_steps=n_steps)
         self._finish(model, frames, generate_video)
         return x
 
@@ -290,7 +302,7 @@ class Diffusion_generation(_DiffusionBase):
                           model_name, multiple_gpus, ema_smoothing)
 
     def sample(self, n, model, target_class=None, cfg_scale=3, input_channels=3, generate_video=False, *, x_T=None,
-               noise=None, use_graph=True):
+               noise=None, use_graph=True, n_steps=None):
         dev = self._native_device()
         frames = [] if generate_video else None
         model.eval()
@@ -299,6 +311,7 @@ class Diffusion_generation(_DiffusionBase):
             # With target_class None the reference evaluates model(x, t, None) twice and lerps a tensor with
             # itself, which returns it unchanged: one unconditional pass is bit-equivalent.
             cfg = target_class is not None and cfg_scale > 0
-            x = self._reverse_process(model, x, None, 1, target_class, cfg, float(cfg_scale), noise, frames, use_graph)
+            x = self._reverse_process(model, x, None, 1, target_class, cfg, float(cfg_scale), noise, frames, use_graph,
+                                      n_steps=n_steps)
         self._finish(model, frames, generate_video)
         return x

@@ -116,12 +116,14 @@ class _NativeHandles:
         self.model = None
         self.stamp = None
         self.plans: Dict[Tuple[int, int, int, int, int], int] = {}
+        self.buffers: Dict[Tuple[int, int, int, int, int], Dict[str, torch.Tensor]] = {}
 
     def release(self):
         lib = N.lib()
         for p in self.plans.values():
             lib.drs_plan_destroy(p)
         self.plans.clear()
+        self.buffers.clear()
         if self.model is not None:
             lib.drs_model_destroy(self.model)
             self.model = None
@@ -132,6 +134,17 @@ class _NativeHandles:
             self.release()
         except Exception:
             pass
+
+    # The handles are raw pointers owned by THIS object: a copied or unpickled module (ema = copy.deepcopy(model))
+    # starts with no native state and packs its own on first use, instead of sharing -- and double-freeing -- these.
+    def __deepcopy__(self, memo):
+        return _NativeHandles()
+
+    def __copy__(self):
+        return _NativeHandles()
+
+    def __reduce__(self):
+        return (_NativeHandles, ())
 
 
 def inv_freq_table() -> torch.Tensor:
@@ -174,7 +187,8 @@ class _NativeUNet(nn.Module):
         h = self.__dict__.get("_native_handles")
         if h is None:
             h = _NativeHandles()
-            self.__dict__["_native_handles"] = h  # not a Module attribute: stays out of state_dict / deepcopy
+            # not a Module attribute: stays out of state_dict; deepcopy / pickle give the copy a fresh empty instance
+            self.__dict__["_native_handles"] = h
         return h
 
     def _stamp(self):
@@ -226,6 +240,22 @@ class _NativeUNet(nn.Module):
             h.plans[key] = out.value
         return h.plans[key]
 
+    def sampler_buffers(self, nb: int, nx: int, ncond: int, S: int, mag: int):
+        """Device buffers (x, z, eps) the sampler of a plan works in. They live as long as the plan, so the CUDA
+        graphs captured on the first sample() -- which hold these addresses -- are replayed by every later one."""
+        self.native_plan(nb, nx, ncond, S, mag)
+        h = self._handles()
+        key = (nb, nx, ncond, S, mag)
+        if key not in h.buffers:
+            dev = self.native_device()
+            d = self._desc()
+            h.buffers[key] = {
+                "x": torch.empty((nx, d.x_channels, S, S), device=dev, dtype=torch.float32),
+                "z": torch.empty((nx, d.x_channels, S, S), device=dev, dtype=torch.float32),
+                "eps": torch.empty((nb, d.out_channels, S, S), device=dev, dtype=torch.float32),
+            }
+        return h.buffers[key]
+
     def release_native(self):
         self._handles().release()
 
@@ -253,6 +283,10 @@ class _NativeUNet(nn.Module):
                 N.check(lib.drs_cond_encode(plan, N.ptr(c32), st))
             lab = None
             if labels is not None:
+                num_classes = getattr(self, "num_classes", None) or 0
+                if labels.numel() and (int(labels.min()) < 0 or int(labels.max()) >= num_classes):
+                    # nn.Embedding raises for these (generate_new_imgs/UNet_model_generation.py:300-301)
+                    raise IndexError("class label out of range [0, %d)" % num_classes)
                 lab = labels.detach().to(dev).to(torch.int32)
                 if lab.numel() == 1 and n > 1:
                     lab = lab.expand(n)

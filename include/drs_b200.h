@@ -120,6 +120,14 @@ int drs_plan_profile(DrsPlan* p, const float* x_dev, float* eps_dev, int iters, 
  * averaged over `iters` evaluations. Synchronises `stream`. */
 int drs_plan_time_forward(DrsPlan* p, const float* x_dev, float* eps_dev, int iters, float* ms_out2, void* stream);
 
+/* Event-timed durations (ms) of the two CUDA-core kernels of a reverse step on a begun sampler, each launch preceded
+ * by an overwrite of the caller's flush buffer (larger than the 126 MB L2; NULL = no flush): ms_out2[0] = conv0
+ * (UNet_model_superres.py:342,355), ms_out2[1] = the posterior update incl. its bookkeeping tail
+ * (train_diffusion_superres.py:240-249). bench.py's HBM roofline entries. Needs more than `iters` steps left; the step
+ * index is restored. Synchronises the stream. */
+int drs_sampler_time_hbm_kernels(DrsPlan* p, void* flush_dev, size_t flush_bytes, int iters, float* ms_out2,
+                                 void* stream);
+
 /* Stand-alone posterior update (train_diffusion_superres.py:240-249), scalars given directly. */
 int drs_ddpm_update(float* x_dev, const float* eps_dev, const float* noise_dev_or_null, float c1, float c2, float c3,
                     size_t numel, void* stream);
@@ -136,37 +144,6 @@ int drs_noise_images(const float* x_dev, const float* eps_dev, const float* sqrt
  * Returns DRS_E_INVALID if some output pixel is covered by no patch (the reference asserts). */
 int drs_blend(const float* patches_dev, const int32_t* coords4_host, int n_patches, const float* weight_dev,
               float* out_dev, float* wsum_dev, int C, int H, int W, int P, int do_clamp, void* stream);
-
-/* Layer-level entry point (tests / INTEGRATION): y = act((conv(x) + bias) * scale + shift) on the tensor-core path.
- * x_dev fp32 NCHW [B,Cin,H,W]; w_host fp32 PyTorch layout; kind: 0 = 3x3 s1 p1, 1 = 3x3 s2 p1, 2 = 1x1,
- * 3 = 2x2 s2 p0, 4 = ConvTranspose2d(3, s2, p1, op1) (weight [Cin,Cout,3,3]). y_dev fp32 NCHW.
- * scale_host / shift_host may be NULL. Synchronises the stream. */
-int drs_debug_conv2d(const float* x_dev, const float* w_host, const float* bias_host, const float* scale_host,
-                     const float* shift_host, float* y_dev, int B, int Cin, int Cout, int H, int W, int kind, int relu,
-                     int device, void* stream);
-
-/* Debug: SM-clock stamps recorded by CTA 0 of the last second-generation convolution launch when the environment
- * variable DRS_V2_TIMELINE is set (8 values per pixel tile: producer start / last issue, MMA after TMEM-empty wait /
- * after first A-full wait / after last issue, epilogue after TMEM-full wait / done). n <= 512. */
-int drs_debug_timeline(long long* out_host, int n);
-/* Debug: with DRS_V2_TIMELINE bit 2 set every second-generation launch records [first CTA entry, last CTA exit] in
- * globaltimer nanoseconds under its launch index. reset != 0 re-arms the table, else it is copied to out_host[128]. */
-int drs_debug_spans(unsigned long long* out_host, int reset);
-
-/* Debug micro-benchmark: one elected thread per CTA issues `iters` (x4 if unroll4) back-to-back tcgen05.mma
- * M=128 x n x K=16 (bf16) on shared-memory operands, `ctas_per_sm` CTAs per SM. out_host[0] = SM cycles until the
- * last instruction was issued, out_host[1] = cycles until all completed (CTA 0). Synchronises the device. */
-int drs_debug_mma_rate(int n, int iters, int unroll4, int ctas_per_sm, long long* out_host);
-
-/* Debug micro-benchmark, second form: `issuers` (1..4) warps of one CTA per SM each issue `iters` K-blocks of `nk`
- * MMAs (M=128 x n x K=16) with the given swizzle `layout` code (2 = 128 B, 4 = 64 B, 6 = 32 B rows) and A group stride
- * `sbo16` (16-byte units). mode 0: descriptors in registers; 1: 32-byte table record per K-block; 2: packed 64-bit
- * record. out_host as above. */
-int drs_debug_mma_rate2(int n, int nk, int layout, int sbo16, int issuers, int iters, int mode, long long* out_host);
-
-/* Intermediate activations of the last forward, converted to fp32 NCHW (tests only). Returns numel written or <0.
- * name: "h0","b0.h","b0.out","d0","b1.out","d1","b2.out","d2","bn.out","g0","psi0","att0","uc0","ut0","x0",... */
-int64_t drs_debug_fetch(DrsPlan* p, const char* name, float* out_dev, int64_t capacity, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,6 @@ for feat, name in ((0x00, "table only (per-iteration record)"), (0x10, "+ nk bra
     iters = 200
     row0 = 0x80 | feat
     code = 1 | (1 << 1) | (80 << 8) | (row0 << 24)
-    N.check(N.lib().drs_debug_mma_rate(n, iters, code, 1, buf))
+    N.check_diag(N.diag_lib().drs_debug_mma_rate(n, iters, code, 1, buf))
     per = 36 if feat else 4
     print(f"{name:36s} N={n}: {buf[1] / (iters * per):7.1f} cyc/MMA")

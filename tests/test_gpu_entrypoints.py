@@ -68,5 +68,36 @@ def test_prepare_scene_and_generate_per_class(cuda_device):
     m, sd = T.default_init_model("generation", seed=2)
     m.to(cuda_device)
     d = D.Diffusion_generation("linear", m, "/nonexistent", noise_steps=4, device=str(cuda_device), image_size=32)
-    out = D.generate_per_class(m, d, 10)
-    assert out.shape == (10, 3, 32, 32) and torch.isfinite(out).all()
+    out = D.generate_per_class(m, d, 10)     # default RNG path; parity: test_gpu_baseline_configs.py
+    assert out.shape == (10, 3, 32, 32) and 0.0 <= out.min().item() and out.max().item() <= 1.0
+
+
+def test_model_copies_own_their_native_state(cuda_device):
+    # ema = copy.deepcopy(model) after a forward must not share (and later double-free) the packed model / plans
+    import copy
+    m, _ = T.default_init_model("sar", seed=3)
+    m.to(cuda_device).eval()
+    x = T.np_randn(13, 2, 1, 32, 32).to(cuda_device)
+    t = torch.full((2,), 5, device=cuda_device)
+    sar = T.np_rand(14, 1, 2, 32, 32).to(cuda_device)
+    with torch.no_grad():
+        a = m(x, t, sar).clone()
+        ema = copy.deepcopy(m)
+        assert ema._handles() is not m._handles() and ema._handles().model is None
+        b = ema(x, t, sar).clone()
+        c = m(x, t, sar).clone()
+    assert torch.equal(a, b) and torch.equal(a, c)
+    del ema
+    import gc
+    gc.collect()
+    with torch.no_grad():
+        assert torch.equal(m(x, t, sar), a)
+
+
+def test_forward_rejects_out_of_range_labels(cuda_device):
+    m, _ = T.default_init_model("generation", seed=2)
+    m.to(cuda_device).eval()
+    x = T.np_randn(15, 2, 3, 32, 32).to(cuda_device)
+    t = torch.full((2,), 5, device=cuda_device)
+    with pytest.raises(IndexError):
+        m(x, t, torch.tensor([3, 10], device=cuda_device))

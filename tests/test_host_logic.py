@@ -72,13 +72,25 @@ def test_product_code_does_not_import_the_oracle():
 
 
 def test_c_abi_exports_every_declared_symbol():
+    # the drop-in boundary (drs_b200.h) and the test / instrumentation hooks (part 2 of drs_b200_diag.h) live in
+    # libdrs_b200.so; the micro-benchmarks (part 1 of drs_b200_diag.h) in their own libdrs_b200_diag.so
+    find = lambda text: set(re.findall(r"\b(drs_[a-z0-9_]+)\s*\(", text))  # noqa: E731
     header = open(os.path.join(T.ROOT, "include", "drs_b200.h")).read()
-    declared = set(re.findall(r"\b(drs_[a-z0-9_]+)\s*\(", header))
-    assert declared, "no declarations found"
-    assert declared == set(N.SIGNATURES), (declared ^ set(N.SIGNATURES))
+    diag = open(os.path.join(T.ROOT, "include", "drs_b200_diag.h")).read()
+    diag_own, diag_hooks = diag.split("hooks inside libdrs_b200.so")
+    boundary, hooks, micro = find(header), find(diag_hooks), find(diag_own)
+    assert boundary and hooks and micro, "no declarations found"
+    assert not any(n.startswith("drs_debug_") for n in boundary), "debug entry points leaked into the boundary header"
+    assert boundary | hooks == set(N.SIGNATURES), ((boundary | hooks) ^ set(N.SIGNATURES))
+    assert micro == set(N.DIAG_SIGNATURES), (micro ^ set(N.DIAG_SIGNATURES))
     lib = ctypes.CDLL(N.LIB_PATH)
-    for name in declared:
+    for name in boundary | hooks:
         assert hasattr(lib, name), name
+    for name in micro:
+        assert not hasattr(lib, name), name + " must not be linked into the product library"
+    dl = ctypes.CDLL(N.DIAG_LIB_PATH)
+    for name in micro:
+        assert hasattr(dl, name), name
     assert lib.drs_version() >= 100
 
 
@@ -152,6 +164,57 @@ def test_patch_sharding_and_gather_world_size_2_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(GLOO_WORKER)
     port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), T.ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
+GLOO_WORKER_EMPTY_BLOCK = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import diffusionremotesensing_b200 as D
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+
+class StubDiffusion:
+    # stands in for Diffusion.sample_batched on a host without a GPU: nearest x2 of the LR patch
+    model = None
+    calls = []
+    def sample_batched(self, model, lr, input_channels=3, **kw):
+        StubDiffusion.calls.append(lr.shape[0])
+        return torch.nn.functional.interpolate(lr, scale_factor=2, mode="nearest")
+
+# (scene side, patch, stride, patch_batch) -> patch counts 1 (fewer patches than ranks: rank 1's block is empty) and 9
+for side, P, s, pb, n_want in ((32, 32, 16, 4, 1), (64, 32, 16, 2, 9)):
+    img = torch.arange(3 * side * side, dtype=torch.float32).reshape(1, 3, side, side)
+    agg = D.split_aggregation_sampling(img, P, s, 2, StubDiffusion(), "cpu", patch_batch=pb)
+    n = len(agg.patches_lr)
+    assert n == n_want, n
+    blocks = D.partition_blocks(n, 2)
+    lo, hi = blocks[rank]
+    StubDiffusion.calls.clear()
+    local = agg.sample_patches(range(lo, hi))
+    assert local.shape == (hi - lo, 3, 2 * P, 2 * P), local.shape
+    # one batch size per block (short batches are padded, the duplicate dropped)
+    assert len(set(StubDiffusion.calls)) <= 1, StubDiffusion.calls
+    out = D.gather_blocks(local, [b - a for a, b in blocks], dst=0)
+    if rank == 0:
+        assert out.shape == (n, 3, 2 * P, 2 * P)
+        for i, (y0, y1, x0, x1) in enumerate(agg.patches_sr_infos):
+            want = torch.nn.functional.interpolate(img[:, :, y0 // 2:y1 // 2, x0 // 2:x1 // 2], scale_factor=2)
+            assert torch.equal(out[i:i + 1], want), i
+    dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_sharded_patch_sampling_with_empty_and_ragged_blocks_gloo(tmp_path):
+    script = tmp_path / "worker2.py"
+    script.write_text(GLOO_WORKER_EMPTY_BLOCK)
+    port = str(31500 + os.getpid() % 2000)
     procs = [subprocess.Popen([sys.executable, str(script), T.ROOT, port, str(r)], stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=180)[0] for p in procs]
