@@ -68,6 +68,7 @@ SIGNATURES = {
                             C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "drs_debug_conv2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "drs_debug_l2_flush": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "drs_debug_timeline": (C.c_int, [C.c_void_p, C.c_int]),
     "drs_debug_spans": (C.c_int, [C.c_void_p, C.c_int]),
     "drs_debug_fetch": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),

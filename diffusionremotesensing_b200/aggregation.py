@@ -10,9 +10,10 @@ Same constructor, public attributes (``patches_lr``, ``patches_sr_infos``, ``wei
     samples its block on its own GPU, one gather brings the finished patches to rank 0, which blends them in the
     reference's patch order and broadcasts the scene. The BLEND is bit-identical whatever the world size; the whole
     scene is bit-identical across world sizes only with injected noise (``noise=`` / ``x_T=`` hooks): without them
-    every rank draws from private generators seeded ``torch.initial_seed() + 1 + first patch index of its block`` so
-    that identically seeded ranks do not reuse one noise stream for different patches (the reference's sequential
-    per-patch RNG stream cannot be reproduced by concurrent chains);
+    every block draws its start states and per-step noise from a private DEVICE generator seeded
+    ``torch.initial_seed() + 1 + first patch index of the block``, so that identically seeded ranks do not reuse one
+    noise stream for different patches (the reference's sequential per-patch CPU / device RNG stream cannot be
+    reproduced by concurrent chains, and a host randn of a whole patch batch would cost more than its sampling);
   * the Gaussian overlap blend, the division and the clamp are one CUDA kernel (``drs_blend``) that accumulates
     each output pixel in patch order with separately rounded fp32 multiply and add, like the reference's
     ``im_res[...] += patch_sr * weight`` sequence.
@@ -61,15 +62,20 @@ def gather_blocks(local: torch.Tensor, counts: Sequence[int], dst: int = 0, grou
 
 
 def blend_patches(patches: torch.Tensor, infos: Sequence[Tuple[int, int, int, int]], weight2d: torch.Tensor,
-                  height: int, width: int, clamp: bool = True):
-    """drs_blend on device tensors: patches [n, C, P, P] fp32, weight2d [P, P] fp32 -> ([1, C, H, W], [H, W])."""
+                  height: int, width: int, clamp: bool = True, out: Optional[torch.Tensor] = None,
+                  wsum: Optional[torch.Tensor] = None, coords: Optional[torch.Tensor] = None):
+    """drs_blend on device tensors: patches [n, C, P, P] fp32, weight2d [P, P] fp32 -> ([1, C, H, W], [H, W]).
+    out / wsum / coords (int32 [n, 4] on the host) may be passed in to reuse buffers across calls."""
     dev = patches.device
     if dev.type != "cuda":
         raise RuntimeError("drs_blend runs on a CUDA device only; there is no CPU fallback")
     n, ch, P, _ = patches.shape
-    coords = torch.tensor([list(i) for i in infos], dtype=torch.int32).contiguous()
-    out = torch.empty((1, ch, height, width), device=dev, dtype=torch.float32)
-    wsum = torch.empty((height, width), device=dev, dtype=torch.float32)
+    if coords is None:
+        coords = torch.tensor([list(i) for i in infos], dtype=torch.int32).contiguous()
+    if out is None:
+        out = torch.empty((1, ch, height, width), device=dev, dtype=torch.float32)
+    if wsum is None:
+        wsum = torch.empty((height, width), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         N.check(N.lib().drs_blend(N.ptr(patches.contiguous()), N.ptr(coords), n, N.ptr(weight2d.contiguous()),
                                   N.ptr(out), N.ptr(wsum), ch, height, width, P, 1 if clamp else 0,
@@ -148,11 +154,10 @@ class split_aggregation_sampling:
         n = len(indices)
         n_batches = -(-n // self.patch_batch)
         size = -(-n // n_batches)
-        gen = cpu_gen = None
+        gen = None
         if private_rng and noise is None:
-            seed = torch.initial_seed() + 1 + indices[0]
-            gen = torch.Generator(device=self.device).manual_seed(seed)
-            cpu_gen = torch.Generator().manual_seed(seed)
+            # start states and per-step noise from one device generator seeded by the block's first patch index
+            gen = torch.Generator(device=self.device).manual_seed(torch.initial_seed() + 1 + indices[0])
         outs = []
         for b0 in range(0, n, size):
             idx = indices[b0:b0 + size]
@@ -161,8 +166,7 @@ class split_aggregation_sampling:
             lr = torch.cat([self.patches_lr[i] for i in idx], dim=0).to(self.device)
             xt = None if x_T is None else torch.cat([x_T(i) for i in idx], dim=0)
             nz = None if noise is None else (lambda step, idx=idx: torch.cat([noise(i, step) for i in idx], dim=0))
-            sr = dm.sample_batched(self.model, lr, input_channels=lr.shape[1], x_T=xt, noise=nz, generator=gen,
-                                   cpu_generator=cpu_gen)
+            sr = dm.sample_batched(self.model, lr, input_channels=lr.shape[1], x_T=xt, noise=nz, generator=gen)
             outs.append(sr[:real])
         return torch.cat(outs, dim=0)
 
@@ -182,7 +186,7 @@ class split_aggregation_sampling:
             patches = gather_blocks(local, [b - a for a, b in blocks], dst=0, group=group)
         else:
             rank = 0
-            patches = self.sample_patches(range(n), noise, x_T)
+            patches = self.sample_patches(range(n), noise, x_T, private_rng=True)
         H, W = height * k, width * k
         if rank == 0:
             im_res, _ = blend_patches(patches, self.patches_sr_infos, self.weight[0, 0], H, W, clamp=True)

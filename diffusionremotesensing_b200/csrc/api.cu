@@ -333,6 +333,15 @@ int drs_debug_conv2d(const float* x_dev, const float* w_host, const float* bias_
   return DRS_OK;
 }
 
+int drs_debug_l2_flush(const void* buf_dev, size_t bytes, void* stream) {
+  if (!buf_dev || bytes < 16) {
+    set_error("drs_debug_l2_flush: bad arguments");
+    return DRS_E_INVALID;
+  }
+  DRS_CUDA(static_cast<cudaError_t>(launch_l2_flush_read(buf_dev, bytes, as_stream(stream))));
+  return DRS_OK;
+}
+
 int drs_debug_spans(unsigned long long* out_host, int reset) {
   const int r = conv_gemm2_spans(out_host, reset);
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "conv_gemm2_spans");

@@ -15,6 +15,7 @@
 #include "../../include/drs_b200.h"
 #include "conv_gemm.cuh"
 #include "conv_gemm2.cuh"
+#include "conv_row.cuh"
 
 namespace drs {
 
@@ -103,6 +104,19 @@ struct GemmSpec {
     int acc_cols = 0;
     uint32_t w_split_off = 0, w_split_bytes = 0;
   } v2;
+
+  // row-streaming program of the same launch (conv_row.cuh): wide low-channel layers, resident weights
+  struct Row {
+    bool usable = false;
+    RowProg prog;
+    int n_sub = 0;
+    uint32_t w_off = 0, w_bytes = 0;   // weight image inside the model's weight blob
+    int a_slot_bytes = 0;
+    int n_pipes = 1;                   // pipelines per CTA
+    int ring_slots = 0;                // S per pipeline
+    int ring_aw[2] = {0, 0};           // accumulator columns per output row of ring 0 / 1
+    int col2 = 0;                      // column offset of the second accumulator seen by the epilogue
+  } row;
 };
 
 struct TimeMlp {
@@ -167,6 +181,12 @@ struct Launch {
   CUtensorMap map_w;
   int grid_c = 0;
   size_t smem_c = 0;
+  // row-streaming kernel (conv_row.cu)
+  bool use_row = false;
+  RowArgs args_r;
+  const RowProg* prog_r = nullptr;
+  int grid_r = 0;
+  size_t smem_r = 0;
 };
 
 }  // namespace drs

@@ -264,7 +264,124 @@ struct Builder {
     g.kb_dev_off = m->kb_all.size();
     m->kb_all.insert(m->kb_all.end(), g.kblocks.begin(), g.kblocks.end());
     build_v2(g, terms);
+    build_row(g, terms);
     return true;
+  }
+
+  // Row-streaming program (conv_row.cuh): 3x3 / 1x1 stride-1 terms, one N split, at most 64 channels per output row
+  // and ring, weights resident. Weight tiles: one per (source channel block, horizontal tap), rows = the three
+  // vertical taps' output channels stacked in the order of the output rows they feed (row above | same row | row
+  // below, i.e. ky = 2, 1, 0), K-major, swizzled like the activation rows.
+  void build_row(GemmSpec& g, const std::vector<ConvTerm>& terms) {
+    GemmSpec::Row& r = g.row;
+    r.usable = false;
+    if (g.nsplit != 1 || g.n_groups != 1 || g.oscale != 1 || g.n_sub > 64) return;
+    if (!conv_row_supports(g.epi_kind, g.flags)) return;
+    int ring_aw[2] = {0, 0};
+    for (const ConvTerm& t : terms) {
+      if (t.kind != CONV_3x3 && t.kind != CONV_1x1) return;
+      if (t.col_slot < 0 || t.col_slot > 1) return;
+      const int aw = g.n_sub * static_cast<int>(t.stack.size());
+      if (ring_aw[t.col_slot] && ring_aw[t.col_slot] != aw) return;
+      ring_aw[t.col_slot] = aw;
+      if (3 * aw > 256) return;
+    }
+    if (!ring_aw[0] || terms.empty() || terms[0].col_slot != 0) return;
+    if (terms[0].kind != CONV_3x3) return;  // pointless for pure 1x1 layers: nothing to stack
+    if (ring_aw[1] && ring_aw[1] != ring_aw[0]) return;  // the epilogue addresses both rings with one slot stride
+    // ring slots per pipeline: a power of two (the kernel indexes the ring with a mask), at least 4 (an output row's
+    // slot is needed again three input rows later). Two pipelines when TMEM holds two such rings.
+    const int cols_per_slot = ring_aw[0] + ring_aw[1];
+    if (4 * cols_per_slot > 512) return;
+    const int n_pipes = (8 * cols_per_slot <= 512) ? 2 : 1;
+    int S = 4;
+    while (2 * S <= kRowMaxRing && 2 * S * cols_per_slot * n_pipes <= 512) S *= 2;
+    memset(&r.prog, 0, sizeof(r.prog));
+    int n_sub = 0, n_mma = 0, max_pix = 0;
+    size_t image = 0;
+    bool ring_seen[2] = {false, false};
+    // pass 1: counts
+    for (const ConvTerm& t : terms) {
+      const int ck = g.src_ck[t.src];
+      const int taps = (t.kind == CONV_3x3) ? 3 : 1;
+      n_sub += t.C / ck;
+      n_mma += taps * (t.C / ck) * (ck / 16);
+    }
+    if (n_sub > kRowMaxSub || n_mma > kRowMaxMma) return;
+    n_sub = n_mma = 0;
+    while (m->wblob.size() % 1024) m->wblob.push_back(0);
+    const size_t w_off = m->wblob.size();
+    for (const ConvTerm& t : terms) {
+      const int ck = g.src_ck[t.src];
+      const int pix = ck * 2;
+      const bool three = (t.kind == CONV_3x3);
+      const int kh = three ? 3 : 1;
+      const int aw = ring_aw[t.col_slot];
+      const int n_grp = three ? 3 : 1;
+      const uint32_t mask = static_cast<uint32_t>(pix / 16 - 1);
+      max_pix = std::max(max_pix, pix);
+      for (int c0 = 0; c0 < t.C; c0 += ck) {
+        RowSub& sub = r.prog.sub[n_sub++];
+        sub.c = c0;
+        sub.bytes = static_cast<uint32_t>((kRowTile + 2) * pix);
+        sub.a_hi = umma_desc_hi(pix, 8 * pix);
+        sub.b_hi = umma_desc_hi(pix, 8 * pix);
+        sub.ring = static_cast<uint16_t>(t.col_slot);
+        sub.aw = static_cast<uint16_t>(aw);
+        sub.src = static_cast<uint8_t>(t.src);
+        sub.rows3 = three ? 1 : 0;
+        sub.first_mma = static_cast<uint8_t>(n_mma);
+        sub.n_mma = static_cast<uint8_t>((three ? 3 : 1) * (ck / 16));
+        for (int dx = 0; dx < (three ? 3 : 1); ++dx) {
+          // the box starts one pixel left of x0: horizontal tap dx reads from pixel dx on (a 1x1 term from pixel 1)
+          const uint32_t a_off16 = static_cast<uint32_t>(((three ? dx : 1) * pix) >> 4);
+          for (int k = 0; k < ck / 16; ++k) {
+            RowMma& mm = r.prog.mma[n_mma++];
+            mm.a_lo = 0x10000u | (a_off16 + 2u * k);
+            mm.b_lo = static_cast<uint32_t>(image >> 4) + 2u * k;
+            mm.grp16 = static_cast<uint32_t>((aw * pix) >> 4);
+            mm.flags = (three ? ROWTAP_3ROWS : 0u) | ((!ring_seen[t.col_slot] && k == 0) ? ROWTAP_RING_FIRST : 0u);
+          }
+          ring_seen[t.col_slot] = true;
+          const size_t tile_bytes = (static_cast<size_t>(n_grp) * aw * pix + 1023) & ~static_cast<size_t>(1023);
+          m->wblob.resize(w_off + image + tile_bytes);
+          uint8_t* tile = m->wblob.data() + w_off + image;
+          for (int gi = 0; gi < n_grp; ++gi) {
+            const int ky = three ? 2 - gi : 0, kx = three ? dx : 0;
+            for (int rr = 0; rr < aw; ++rr) {
+              const WeightRef& wr = t.stack[rr / g.n_sub];
+              const int oc = rr % g.n_sub;
+              const int row = gi * aw + rr;
+              for (int k = 0; k < ck; ++k) {
+                const int ci = wr.ci_off + c0 + k;
+                const float val = wr.w[((static_cast<size_t>(oc) * wr.cin_total + ci) * kh + ky) * kh + kx];
+                uint32_t o = static_cast<uint32_t>(row * pix + k * 2);
+                o ^= ((o >> 7) & mask) << 4;
+                const uint16_t h = f32_to_bf16(val);
+                memcpy(tile + o, &h, 2);
+              }
+            }
+          }
+          image += tile_bytes;
+        }
+      }
+    }
+    r.n_sub = n_sub;
+    r.w_off = static_cast<uint32_t>(w_off);
+    r.w_bytes = static_cast<uint32_t>(image);
+    r.a_slot_bytes = ((kRowTile + 2) * max_pix + 1023) & ~1023;
+    r.ring_slots = S;
+    r.n_pipes = n_pipes;
+    r.ring_aw[0] = ring_aw[0];
+    r.ring_aw[1] = ring_aw[1];
+    r.col2 = ring_aw[1] ? S * ring_aw[0] : g.col2;
+    // resident weights + at least max(3, 2 sub-tiles) A slots per pipeline + the store staging must fit
+    const size_t need = image + static_cast<size_t>(n_pipes) * std::max(3, 2 * n_sub) * r.a_slot_bytes + kStageBytes;
+    if (need > 200 * 1024) {
+      m->wblob.resize(w_off);
+      return;
+    }
+    r.usable = true;
   }
 
   // Halo-tile program of the same launch (conv_gemm2.cuh). K-blocks are ordered sub-tile major: all taps that read
@@ -837,6 +954,7 @@ int model_create(const DrsModelDesc* desc, const DrsTensor* tensors, int n_tenso
   int r = conv_gemm_set_smem_limits();
   if (r == 0) r = conv_gemm2_set_smem_limits();
   if (r == 0) r = conv_gemm2c_set_smem_limits();
+  if (r == 0) r = conv_row_set_smem_limits();
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "cudaFuncSetAttribute(conv_gemm_kernel)");
   // the host copy of the state_dict is no longer needed
   m->sd.clear();
@@ -883,6 +1001,7 @@ int build_debug_conv(DrsModel* m, const float* w, const float* bias, const float
   int r = conv_gemm_set_smem_limits();
   if (r == 0) r = conv_gemm2_set_smem_limits();
   if (r == 0) r = conv_gemm2c_set_smem_limits();
+  if (r == 0) r = conv_row_set_smem_limits();
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "cudaFuncSetAttribute(conv_gemm_kernel)");
   return DRS_OK;
 }

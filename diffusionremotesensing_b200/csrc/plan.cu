@@ -400,8 +400,94 @@ static int bind_launch_cg2(DrsPlan* p, Launch* L) {
   return DRS_OK;
 }
 
+// Row-streaming binding (conv_row.cu): full-width stride-1 layers with at most 64 output channels whose pixel grid is
+// a multiple of 128 wide and tall enough to give every SM a dozen rows; takes precedence over the second-generation
+// kernel. DRS_ROW=0 disables it, DRS_ROW=force drops the size threshold (layer-level tests).
+static int bind_launch_row(DrsPlan* p, const void* src0, const void* src1, int gridW, int gridH, int srcH[2],
+                           int srcW[2], Launch* L) {
+  const DrsModel* m = p->m;
+  const GemmSpec& g = m->gemms[L->spec];
+  const GemmSpec::Row& r = g.row;
+  L->use_row = false;
+  static const char* const env = getenv("DRS_ROW");
+  const bool disabled = env && env[0] == '0';
+  const bool force = env && env[0] == 'f';
+  if (disabled || !r.usable || gridW % kRowTile || gridH < 4) return DRS_OK;
+  for (int s = 0; s < g.n_src; ++s)
+    if (g.src_stride2[s] || srcH[s] != gridH || srcW[s] != gridW) return DRS_OK;
+  const int sms = sm_count(m->device);
+  const long long tiles = static_cast<long long>(p->nb) * (gridW / kRowTile) * gridH;
+  if (!force && tiles < 12LL * sms) return DRS_OK;  // short ranges pay two halo rows each: the tile kernel wins
+  RowArgs& a = L->args_r;
+  memset(&a, 0, sizeof(a));
+  a.wimage = m->d_wblob.as<uint8_t>() + r.w_off;
+  a.w_bytes = r.w_bytes;
+  a.n_sub = r.n_sub;
+  a.W = gridW;
+  a.H = gridH;
+  a.B = p->nb;
+  a.tiles_x = gridW / kRowTile;
+  a.a_slot_bytes = r.a_slot_bytes;
+  // two pipelines only when each still gets a dozen rows (every range re-reads two halo rows)
+  static const char* const pipes_env = getenv("DRS_ROW_PIPES");
+  const int n_pipes = pipes_env ? std::max(1, std::min(r.n_pipes, atoi(pipes_env)))
+                                : ((tiles >= 24LL * sms) ? r.n_pipes : 1);
+  a.n_pipes = n_pipes;
+  a.ring_slots = r.ring_slots;
+  a.ring_aw[0] = r.ring_aw[0];
+  a.ring_aw[1] = r.ring_aw[1];
+  a.tmem_cols = 512;
+  a.n_acc = g.n_sub;
+  a.err = p->d_err;
+  {
+    static const int timeline = getenv("DRS_V2_TIMELINE") ? atoi(getenv("DRS_V2_TIMELINE")) : 0;
+    static const char* const tl_layer = getenv("DRS_V2_TIMELINE_LAYER");
+    a.timeline = ((timeline & 1) && (!tl_layer || g.name.find(tl_layer) != std::string::npos))
+                     ? conv_gemm2_timeline_dev() : nullptr;
+  }
+  a.epi = L->args.epi;
+  a.epi.col2 = r.col2;
+  a.epi.n_groups = 1;
+  const bool stage = (g.epi_kind == EPI_STD);
+  const int stage_bytes = stage ? kStageBytes : 0;
+  const int w_pad = static_cast<int>((r.w_bytes + 1023u) & ~1023u);
+  const int budget = 227 * 1024 - 16 * 1024 - w_pad - stage_bytes;
+  const int slots = std::min(kRowMaxASlots, budget / r.a_slot_bytes / n_pipes);  // per pipeline
+  if (slots < std::max(3, 2 * r.n_sub)) return DRS_OK;
+  a.a_slots = slots;
+  const void* srcs[2] = {src0, src1};
+  CUtensorMap maps[2];
+  for (int s = 0; s < g.n_src; ++s)
+    DRS_TRY(make_map(&maps[s], srcs[s], p->nb, srcH[s], srcW[s], g.src_C[s], false, g.src_ck[s], kRowTile + 2, 1, 1));
+  CUtensorMap out_map = maps[0];
+  a.store_sbc = 0;
+  if (stage) {
+    a.store_sbc = std::min(64, g.n_sub);
+    DRS_TRY(make_map(&out_map, a.epi.out, p->nb, a.epi.OH, a.epi.OW, a.epi.OC, false, a.store_sbc, 32, 1, 1));
+  }
+  L->map0 = maps[0];
+  L->map1 = (g.n_src == 2) ? maps[1] : maps[0];
+  L->map_out = out_map;
+  L->prog_r = &r.prog;
+  L->smem_r = static_cast<size_t>(slots) * n_pipes * r.a_slot_bytes + w_pad + stage_bytes + 1024;
+  L->grid_r = static_cast<int>(std::min<long long>(sms, std::max<long long>(1, tiles / (4 * n_pipes))));
+  L->use_row = true;
+  L->use_v2 = false;
+  L->use_cg2 = false;
+  static const bool verbose = (getenv("DRS_V2_VERBOSE") != nullptr);
+  if (verbose)
+    fprintf(stderr, "[drs] %s: row kernel, %d CTAs x %d pipelines, %d A slots of %d B each, weights %u B, ring %d slots, smem %zu\n",
+            g.name.c_str(), L->grid_r, n_pipes, slots, r.a_slot_bytes, r.w_bytes, r.ring_slots, L->smem_r);
+  return DRS_OK;
+}
+
 static int launch_one(const DrsPlan* p, const Launch& L, float* eps, cudaStream_t st) {
   const GemmSpec& g = p->m->gemms[L.spec];
+  if (L.use_row) {
+    RowArgs a = L.args_r;
+    if (g.epi_kind == EPI_OUT && eps) a.epi.out = eps;
+    return launch_conv_row(g.epi_kind, L.map0, L.map1, L.map_out, a, *L.prog_r, L.grid_r, L.smem_r, st);
+  }
   if (L.use_cg2)
     return launch_conv_gemm2c(L.map0, L.map1, L.map_out, L.map_w, L.args_c, L.prog_c, L.grid_c, L.smem_c, st);
   if (L.use_v2) {
@@ -545,6 +631,7 @@ int plan_create(DrsModel* m, int nb, int nx, int ncond, int S, int mag, DrsPlan*
     if (g.flags & F_ROWSCALE) L.args.epi.psi = reinterpret_cast<const float*>(ws + p->acts.at(g.src_name[1]).offset);
     DRS_TRY(bind_launch_v2(p.get(), src[0], src[1], gridW, gridH, sH, sW, &L));
     DRS_TRY(bind_launch_cg2(p.get(), &L));
+    if (!(g.flags & F_ROWSCALE)) DRS_TRY(bind_launch_row(p.get(), src[0], src[1], gridW, gridH, sH, sW, &L));
     p->launches.push_back(L);
   }
   *out = p.release();
@@ -667,6 +754,7 @@ static void rebind_table(DrsPlan* p) {
     L.args.epi.te = p->table.as<float>();
     L.args2.epi.te = p->table.as<float>();
     L.args_c.epi.te = p->table.as<float>();
+    L.args_r.epi.te = p->table.as<float>();
   }
 }
 
@@ -976,7 +1064,7 @@ int sampler_step(DrsPlan* p, int use_graph, cudaStream_t st) {
 }
 
 // Event-timed durations of the two CUDA-core kernels of a reverse step, each launch on a cold L2 (the caller's flush
-// buffer, larger than L2, is overwritten before every timed launch): ms_out[0] = conv0, ms_out[1] = posterior update
+// buffer, larger than L2, is read before every timed launch, which leaves the L2 cold and clean): ms_out[0] = conv0, ms_out[1] = posterior update
 // with its bookkeeping tail. The sampler's step index is restored afterwards.
 int sampler_time_hbm_kernels(DrsPlan* p, void* flush_dev, size_t flush_bytes, int iters, float* ms_out,
                              cudaStream_t st) {
@@ -993,14 +1081,14 @@ int sampler_time_hbm_kernels(DrsPlan* p, void* flush_dev, size_t flush_bytes, in
   double acc[2] = {0.0, 0.0};
   int rc = DRS_OK;
   for (int it = 0; it < iters && rc == DRS_OK; ++it) {
-    if (flush_dev) cudaMemsetAsync(flush_dev, it & 0xFF, flush_bytes, st);
+    if (flush_dev) launch_l2_flush_read(flush_dev, flush_bytes, st);
     cudaEventRecord(ev[0], st);
     int r = launch_conv0(p->x, m->fblob.data() + m->conv0.w, m->fblob.data() + m->conv0.b,
                          m->has_cond ? p->cond_feat.as<float>() : nullptr, p->workspace.as<uint8_t>() + h0.offset,
                          p->nb, p->nx, m->has_cond ? p->ncond : 1, m->desc.x_channels, p->S, st);
     cudaEventRecord(ev[1], st);
     if (r != 0) rc = cuda_fail(static_cast<cudaError_t>(r), "conv0 (timing)");
-    if (flush_dev) cudaMemsetAsync(flush_dev, (it + 1) & 0xFF, flush_bytes, st);
+    if (flush_dev) launch_l2_flush_read(flush_dev, flush_bytes, st);
     cudaEventRecord(ev[2], st);
     r = launch_ddpm_update(p->x, p->eps, p->noise, p->d_coef, p->d_step, numel, cfg, p->cfg_scale, p->d_trow, p->nb,
                            p->n_uniq, p->d_step + 1, st);
@@ -1030,6 +1118,7 @@ int debug_bind_and_run(DrsPlan* p, const void* in, int gridW, int gridH, int src
   DRS_TRY(bind_launch(p, 0, in, nullptr, gridW, gridH, sH, sW, out, OH, OW, &L));
   DRS_TRY(bind_launch_v2(p, in, nullptr, gridW, gridH, sH, sW, &L));
   DRS_TRY(bind_launch_cg2(p, &L));
+  DRS_TRY(bind_launch_row(p, in, nullptr, gridW, gridH, sH, sW, &L));
   const int r = launch_one(p, L, nullptr, st);
   if (r != 0) return cuda_fail(static_cast<cudaError_t>(r), "launch_conv_gemm(debug)");
   return DRS_OK;
@@ -1089,8 +1178,9 @@ int launch_info(const DrsPlan* p, int i, char* name, int name_cap, double* flops
       b += grid_px * g.oscale * g.oscale * g.OC * 2;
     *bytes = b;
   }
-  if (ctas) *ctas = L.use_cg2 ? -L.grid_c : (L.use_v2 ? -L.grid2 : L.n_tiles * g.nsplit);  // negative: persistent grid
-  if (smem_bytes) *smem_bytes = static_cast<int>(L.use_cg2 ? L.smem_c : L.smem);
+  // negative: persistent grid (row kernel: -10000 - grid)
+  if (ctas) *ctas = L.use_row ? -10000 - L.grid_r : (L.use_cg2 ? -L.grid_c : (L.use_v2 ? -L.grid2 : L.n_tiles * g.nsplit));
+  if (smem_bytes) *smem_bytes = static_cast<int>(L.use_row ? L.smem_r : (L.use_cg2 ? L.smem_c : L.smem));
   return DRS_OK;
 }
 

@@ -372,8 +372,8 @@ __device__ __forceinline__ float lerp_aten(float u, float c, float w) {
 // still needs the old value: it decrements the step index and the time-table rows and re-arms the counter.
 // Each thread owns kUpdU float4 quads a block-stride apart and issues all of its loads before the first use, so one
 // round trip to HBM covers the whole kernel (the r1 form ran four dependent round trips per block: step, coefficient,
-// data, fence + atomic). `step` and the coefficient row were written at least one whole launch earlier, so they are
-// read BEFORE griddepcontrol.wait and overlap the tail of the preceding convolution.
+// data, fence + atomic). `step` was written at least one whole launch earlier, so it is read BEFORE
+// griddepcontrol.wait and overlaps the tail of the preceding convolution.
 constexpr int kUpdU = 4;
 template <bool CFG>
 __global__ void __launch_bounds__(256, CFG ? 3 : 4)
@@ -382,7 +382,7 @@ ddpm_update_kernel(float* __restrict__ x, const float* __restrict__ eps, const f
                    int n_rows, int row_dec, int* counter) {
   constexpr bool cfg = CFG;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const float4 cf = __ldg(reinterpret_cast<const float4*>(coef) + *reinterpret_cast<volatile int*>(step));
+  const int step_now = *reinterpret_cast<volatile int*>(step);
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const bool has_z = (noise != nullptr);
   const size_t base = static_cast<size_t>(blockIdx.x) * (256 * kUpdU) + threadIdx.x;
@@ -399,6 +399,8 @@ ddpm_update_kernel(float* __restrict__ x, const float* __restrict__ eps, const f
       if (has_z) zv[u] = __ldcs(reinterpret_cast<const float4*>(noise) + i);
     }
   }
+  // the coefficient row is fetched behind the data loads (its latency hides under theirs)
+  const float4 cf = __ldg(reinterpret_cast<const float4*>(coef) + step_now);
 #pragma unroll
   for (int u = 0; u < kUpdU; ++u) {
     const size_t i = base + static_cast<size_t>(u) * 256;
@@ -561,6 +563,24 @@ int launch_blend_gather(const float* patches, const int* ys, int ny, const int* 
 // a pixel quad come from two small range tables built on the host ((first, last + 1) indices into the sorted start
 // lists), so nothing is scanned. Patches are visited in row-major patch order and every pixel is accumulated with a
 // separately rounded multiply and add, exactly like the scalar kernel and the reference's `+=` sequence.
+// 50 registers, five blocks per SM: 168 us = 6.1 TB/s (0.93 of the measured copy bandwidth) at the cfg-5 shape. (A
+// variant that issued the loads of all of a pixel's patches before the first add needed 88 registers, two blocks per
+// SM, and ran at 246 us.)
+template <int C>
+__device__ __forceinline__ void blend_accumulate4(float4 (&acc)[C], float4& cnt, const float4 (&v)[C], const float4& w) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    acc[c].x = __fadd_rn(acc[c].x, __fmul_rn(v[c].x, w.x));
+    acc[c].y = __fadd_rn(acc[c].y, __fmul_rn(v[c].y, w.y));
+    acc[c].z = __fadd_rn(acc[c].z, __fmul_rn(v[c].z, w.z));
+    acc[c].w = __fadd_rn(acc[c].w, __fmul_rn(v[c].w, w.w));
+  }
+  cnt.x = __fadd_rn(cnt.x, w.x);
+  cnt.y = __fadd_rn(cnt.y, w.y);
+  cnt.z = __fadd_rn(cnt.z, w.z);
+  cnt.w = __fadd_rn(cnt.w, w.w);
+}
+
 template <int C>
 __global__ void __launch_bounds__(256)
 blend_gather4_kernel(const float* __restrict__ patches, const int* __restrict__ ys, const int* __restrict__ xs, int nx,
@@ -578,27 +598,19 @@ blend_gather4_kernel(const float* __restrict__ patches, const int* __restrict__ 
   for (int c = 0; c < C; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 cnt = make_float4(0.f, 0.f, 0.f, 0.f);
   const size_t pp = static_cast<size_t>(P) * P;
-  for (int iy = ry.x; iy < ry.y; ++iy) {
-    const int ly = Y - __ldg(ys + iy);
-    for (int ix = cx.x; ix < cx.y; ++ix) {
-      const int lx = X - __ldg(xs + ix);
-      const size_t o = static_cast<size_t>(ly) * P + lx;
-      const float4 w = __ldg(reinterpret_cast<const float4*>(weight + o));
-      const float* pb = patches + static_cast<size_t>(iy * nx + ix) * C * pp + o;
-      float4 v[C];
+  {
+    for (int iy = ry.x; iy < ry.y; ++iy) {
+      const int ly = Y - __ldg(ys + iy);
+      for (int ix = cx.x; ix < cx.y; ++ix) {
+        const int lx = X - __ldg(xs + ix);
+        const size_t o = static_cast<size_t>(ly) * P + lx;
+        const float4 w = __ldg(reinterpret_cast<const float4*>(weight + o));
+        const float* pb = patches + static_cast<size_t>(iy * nx + ix) * C * pp + o;
+        float4 v[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) v[c] = __ldcs(reinterpret_cast<const float4*>(pb + c * pp));
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        acc[c].x = __fadd_rn(acc[c].x, __fmul_rn(v[c].x, w.x));
-        acc[c].y = __fadd_rn(acc[c].y, __fmul_rn(v[c].y, w.y));
-        acc[c].z = __fadd_rn(acc[c].z, __fmul_rn(v[c].z, w.z));
-        acc[c].w = __fadd_rn(acc[c].w, __fmul_rn(v[c].w, w.w));
+        for (int c = 0; c < C; ++c) v[c] = __ldcs(reinterpret_cast<const float4*>(pb + c * pp));
+        blend_accumulate4<C>(acc, cnt, v, w);
       }
-      cnt.x = __fadd_rn(cnt.x, w.x);
-      cnt.y = __fadd_rn(cnt.y, w.y);
-      cnt.z = __fadd_rn(cnt.z, w.z);
-      cnt.w = __fadd_rn(cnt.w, w.w);
     }
   }
   const size_t po = static_cast<size_t>(Y) * W + X;
@@ -672,6 +684,24 @@ int launch_blend_finalize(float* acc, const float* wsum, int C, int H, int W, in
                           cudaStream_t s) {
   const size_t HW = static_cast<size_t>(H) * W;
   blend_finalize_kernel<<<cdiv(static_cast<long long>(HW), 256), 256, 0, s>>>(acc, wsum, C, HW, do_clamp, zero_flag);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// L2 flush for cold-cache timing: READS a buffer larger than L2 (a memset would leave the L2 full of dirty lines whose
+// write-back then competes with the kernel being timed)
+// ------------------------------------------------------------------------------------------------
+__global__ void l2_flush_read_kernel(const uint4* __restrict__ buf, size_t n16, unsigned* sink) {
+  unsigned acc = 0;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = __ldg(buf + i);
+    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+  }
+  if (acc == 0x9E3779B9u && sink) *sink = acc;  // practically never: keeps the loads alive
+}
+int launch_l2_flush_read(const void* buf, size_t bytes, cudaStream_t s) {
+  l2_flush_read_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<const uint4*>(buf), bytes / 16, nullptr);
   return static_cast<int>(cudaGetLastError());
 }
 

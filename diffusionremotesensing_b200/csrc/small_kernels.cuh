@@ -58,6 +58,9 @@ int launch_blend_accumulate(const float* patch, const float* weight, float* acc,
 int launch_blend_finalize(float* acc, const float* wsum, int C, int H, int W, int do_clamp, int* zero_flag,
                           cudaStream_t s);
 
+// Reads `bytes` of a buffer (larger than L2) so that the next kernel starts on a cold, clean L2 (timing only).
+int launch_l2_flush_read(const void* buf, size_t bytes, cudaStream_t s);
+
 // fp32 NCHW <-> bf16 NHWC converters (debug / layer-level entry points)
 int launch_nchw_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, cudaStream_t s);
 int launch_nhwc_bf16_to_nchw(const void* in, float* out, int B, int C, int H, int W, cudaStream_t s);

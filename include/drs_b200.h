@@ -121,7 +121,7 @@ int drs_plan_profile(DrsPlan* p, const float* x_dev, float* eps_dev, int iters, 
 int drs_plan_time_forward(DrsPlan* p, const float* x_dev, float* eps_dev, int iters, float* ms_out2, void* stream);
 
 /* Event-timed durations (ms) of the two CUDA-core kernels of a reverse step on a begun sampler, each launch preceded
- * by an overwrite of the caller's flush buffer (larger than the 126 MB L2; NULL = no flush): ms_out2[0] = conv0
+ * by a read of the caller's flush buffer (larger than the 126 MB L2, leaves it cold and clean; NULL = no flush): ms_out2[0] = conv0
  * (UNet_model_superres.py:342,355), ms_out2[1] = the posterior update incl. its bookkeeping tail
  * (train_diffusion_superres.py:240-249). bench.py's HBM roofline entries. Needs more than `iters` steps left; the step
  * index is restored. Synchronises the stream. */

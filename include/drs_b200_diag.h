@@ -49,6 +49,10 @@ int drs_debug_conv2d(const float* x_dev, const float* w_host, const float* bias_
  * name: "h0","b0.h","b0.out","d0","b1.out","d1","b2.out","d2","bn.out","g0","psi0","att0","uc0","ut0","x0",... */
 int64_t drs_debug_fetch(DrsPlan* p, const char* name, float* out_dev, int64_t capacity, void* stream);
 
+/* Timing aid: reads `bytes` (more than the 126 MB L2) of a device buffer on `stream`, so the next kernel starts on a
+ * cold L2 that holds no dirty lines (a memset flush leaves write-backs that compete with the kernel being timed). */
+int drs_debug_l2_flush(const void* buf_dev, size_t bytes, void* stream);
+
 /* Debug: SM-clock stamps recorded by CTA 0 of the last second-generation convolution launch when the environment
  * variable DRS_V2_TIMELINE is set (8 values per pixel tile: producer start / last issue, MMA after TMEM-empty wait /
  * after first A-full wait / after last issue, epilogue after TMEM-full wait / done). n <= 512. */

@@ -64,6 +64,14 @@ CASES = [
     ("T3x3s2", 2, 64, 64, 16, 16),
     ("T3x3s2", 1, 256, 256, 8, 8),
     ("T3x3s2", 2, 128, 128, 12, 20),
+    # full-width rows (multiples of 128 pixels, <= 64 output channels): the shapes the row-streaming kernel takes
+    # (conv_row.cu; by default only above a size threshold, with DRS_ROW=force always -- test_gpu_kernel_variants.py)
+    ("3x3", 2, 16, 32, 24, 128),
+    ("3x3", 1, 32, 32, 40, 256),
+    ("3x3", 3, 64, 64, 17, 128),     # odd row count: ranges end inside a strip
+    ("3x3", 2, 64, 32, 5, 256),
+    ("3x3", 1, 32, 64, 4, 128),
+    ("3x3", 4, 16, 16, 33, 256),
 ]
 
 
@@ -93,7 +101,7 @@ def test_conv_matches_torch(cuda_device, kind, B, Cin, Cout, H, W):
 
 
 @pytest.mark.parametrize("kind,B,Cin,Cout,H,W", [("3x3s2", 16, 64, 64, 128, 128), ("3x3", 16, 64, 64, 128, 128),
-                                                 ("T3x3s2", 16, 64, 64, 64, 64)])
+                                                 ("T3x3s2", 16, 64, 64, 64, 64), ("3x3", 8, 64, 32, 256, 256)])
 def test_persistent_kernel_is_deterministic_and_correct_on_many_tiles(cuda_device, kind, B, Cin, Cout, H, W):
     """Many pixel tiles per persistent CTA (tile pairs, odd tile counts, shared-memory ring reuse): the result must be
     bit-identical from launch to launch and match torch. Regression test for a ring-phase race that corrupted the

@@ -8,6 +8,8 @@ path (tests/test_gpu_conv_layers.py):
   * DRS_V2_NO_SOLO=1        transposed convolutions drained by one epilogue group per tile
   * DRS_DISABLE_V2=1        first-generation kernel for every layer
   * DRS_NO_NARROW=1         no 32-channel launch variants on small grids (the default test sizes otherwise use them)
+  * DRS_ROW=force / DRS_ROW=0  row-streaming kernel (conv_row.cu) on every layer it can express whatever the grid
+                            size / on none (the second-generation kernel for everything)
 """
 import os
 import subprocess
@@ -53,3 +55,17 @@ def test_cta_pair_kernel_unet_and_sampler_parity(cuda_device):
 def test_unet_parity_without_narrow_variants(cuda_device):
     r = run_child({"DRS_NO_NARROW": "1"}, ["tests/test_gpu_unet.py"])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_row_kernel_layer_and_unet_parity_forced(cuda_device):
+    r = run_child({"DRS_ROW": "force"}, ["tests/test_gpu_conv_layers.py", "tests/test_gpu_unet.py",
+                                         "tests/test_gpu_sampler.py"])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "row kernel" in r.stderr or "row kernel" in r.stdout, "no launch used the row-streaming kernel"
+
+
+def test_parity_without_row_kernel(cuda_device):
+    r = run_child({"DRS_ROW": "0"}, ["tests/test_gpu_unet.py", "tests/test_gpu_full_size.py::test_full_resolution_eps_matches_oracle",
+                                     "tests/test_gpu_baseline_configs.py::test_cfg2_batch16_trajectory_vs_oracle"])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "row kernel" not in r.stderr and "row kernel" not in r.stdout
