@@ -20,6 +20,21 @@
 
 namespace drs {
 
+// Barrier wait of this kernel: the poll inline, the bounded back-off loop out of line. The issuer's per-row path has to
+// stay small -- with ptx.cuh's fully inlined wait (sixteen unrolled try / sleep rounds at each of its eight call sites)
+// one row walked through several KiB of code and ran at ~18 cycles per instruction (instruction-cache misses).
+__device__ __noinline__ void row_wait_slow(uint64_t* bar, uint32_t parity, int* err, int code) {
+  for (int tries = 0; tries < (1 << 15); ++tries) {
+    if (mbar_try_wait_hint(bar, parity, 20000u)) return;
+    if (err && (tries & 15) == 15 && *reinterpret_cast<volatile int*>(err) != 0) return;
+  }
+  if (err) atomicCAS(err, 0, code);
+}
+__device__ __forceinline__ void row_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  row_wait_slow(bar, parity, err, code);
+}
+
 struct RowRing {
   int idx;
   uint32_t phase;
@@ -52,14 +67,31 @@ struct RowWalk {
   }
 };
 
-// Debug timeline (DRS_V2_TIMELINE=1): pipeline 0 of CTA 0, first 64 rows it touches, 8 slots per row --
+// Debug timeline (DRS_V2_TIMELINE=1): pipeline 0 of CTA 0, first 32 rows it touches, 16 slots per row --
 // 0 issuer at row start, 1 after the ring-slot (empty) waits, 2 after the first A-full wait, 3 after the last MMA issue,
 // 4 producer after the A-empty wait of the row's first sub-tile, 5 epilogue before / 6 after the accumulator-full wait,
-// 7 epilogue done. Issuer / producer rows count input rows, epilogue rows count output rows.
+// 7 epilogue done; issuer detail: 8 after the run construction (before the ring-slot waits), 9 / 10 / 11 first
+// sub-tile after elect / after its MMAs / after its commit, 12 after the output-row commits.
+// Issuer / producer rows count input rows, epilogue rows count output rows.
 #define RTL(row_no, slot)                                                                                      \
   do {                                                                                                         \
-    if (a.timeline && blockIdx.x == 0 && pipe == 0 && (row_no) < 64) a.timeline[(row_no) * 8 + (slot)] = clock64(); \
+    if (a.timeline && blockIdx.x == 0 && pipe == 0 && (row_no) < 32) a.timeline[(row_no) * 16 + (slot)] = clock64(); \
   } while (0)
+
+// The three horizontal taps of one 3x3 sub-tile against one run of output rows: 3 * NK MMAs whose descriptors were all
+// formed before the first one is issued (a record fetched, added and moved to the uniform datapath per MMA costs the
+// issuing thread ~250 cycles of dependent latency; formed up front the chains overlap).
+template <int NK>
+__device__ __forceinline__ void row_issue3(uint32_t d, uint32_t idesc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b0,
+                                           uint32_t b1, uint32_t b2, uint32_t a_hi, uint32_t b_hi, uint32_t skip_first) {
+  umma_bf16_split_if(skip_first == 0u, d, a0, a_hi, b0, b_hi, idesc, 1u);
+#pragma unroll
+  for (int k = 1; k < NK; ++k) umma_bf16_split(d, a0 + 2u * k, a_hi, b0 + 2u * k, b_hi, idesc, 1u);
+#pragma unroll
+  for (int k = 0; k < NK; ++k) umma_bf16_split(d, a1 + 2u * k, a_hi, b1 + 2u * k, b_hi, idesc, 1u);
+#pragma unroll
+  for (int k = 0; k < NK; ++k) umma_bf16_split(d, a2 + 2u * k, a_hi, b2 + 2u * k, b_hi, idesc, 1u);
+}
 
 constexpr int kRowIssuerWarp0 = kRowEpiWarps;                 // issuer of pipeline p: kRowIssuerWarp0 + p
 constexpr int kRowProducerWarp0 = kRowEpiWarps + kRowPipes;   // producer of pipeline p
@@ -83,6 +115,12 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const EpiArgs& e = a.epi;
   const int n_pipes = a.n_pipes;
+  // debug (DRS_V2_TIMELINE=8): globaltimer at entry / exit of every CTA
+  if (a.cta_times && threadIdx.x == 0 && blockIdx.x < 256) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.cta_times[2 * blockIdx.x] = static_cast<long long>(t);
+  }
   // role -> pipeline: epilogue warps 0..3 / 4..7 serve pipeline 0 / 1 (or alternate rows of the only pipeline)
   int pipe = 0;
   if (warp >= kRowProducerWarp0) pipe = warp - kRowProducerWarp0;
@@ -157,19 +195,21 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         const int yi_lo = max(sg.r0 - 1, 0), yi_hi = min(sg.r1, a.H - 1);
         for (int yi = yi_lo; yi <= yi_hi; ++yi, ++row_no) {
           const bool centre = (yi >= sg.r0) && (yi < sg.r1);
-          for (int s = 0; s < a.n_sub; ++s) {
-            const RowSub T = prog.sub[s];
-            if (!T.rows3 && !centre) continue;  // a 1x1 term has no use for the halo rows
-            mbar_wait(&aempty[ar.idx], ar.phase ^ 1u, a.err, 1);
-            if (s == 0 && lane == 0) RTL(row_no, 4);
-            if (elect_one()) {
-              mbar_expect_tx(&afull[ar.idx], T.bytes);
-              tma_load_5d(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes, T.src ? &map1 : &map0, &afull[ar.idx],
-                          T.c, sg.x0 - 1, 0, yi, sg.b);
+          // one row slot = every sub-tile of this input row, one barrier (a 1x1 term has no use for the halo rows)
+          row_wait(&aempty[ar.idx], ar.phase ^ 1u, a.err, 1);
+          if (lane == 0) RTL(row_no, 4);
+          if (elect_one()) {
+            uint8_t* const slot = a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes;
+            mbar_expect_tx(&afull[ar.idx], centre ? a.row_bytes_all : a.row_bytes3);
+            for (int s = 0; s < a.n_sub; ++s) {
+              const RowSub T = prog.sub[s];
+              if (!T.rows3 && !centre) continue;
+              tma_load_5d(slot + (static_cast<uint32_t>(T.off_kib) << 10), T.src ? &map1 : &map0, &afull[ar.idx], T.c,
+                          sg.x0 - 1, 0, yi, sg.b);
             }
-            __syncwarp();
-            ar.advance(a.a_slots);
           }
+          __syncwarp();
+          ar.advance(a.a_slots);
         }
       }
     }
@@ -180,10 +220,25 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     // consecutive ring slots; per MMA the issuing lane reads one 128-bit record and does three adds. (A first
     // version recomputed slots with integer divisions inside the MMA loop: ~1000 cycles per MMA on one thread.)
     if (pipe < n_pipes) {
-      mbar_wait(&s_wready, 0, a.err, 2);
+      row_wait(&s_wready, 0, a.err, 2);
       RowRing ar{0, 0};
       const uint32_t wb = 0x10000u | (smem_u32(w_base) >> 4);
       const uint32_t idesc0 = umma_idesc_bf16(kRowTile, 0);
+      const uint32_t aw0 = static_cast<uint32_t>(a.ring_aw[0]), aw1 = static_cast<uint32_t>(a.ring_aw[1]);
+      const uint32_t d_ring0 = tmem + ring0_col, d_ring1 = tmem + ring1_col;
+      const RowSub T0 = prog.sub[0], T1 = prog.sub[1];  // the first two sub-tile records stay in registers
+      // ... and so do the tap records of the first two sub-tiles when they are 3x3 terms (weight offsets already
+      // rebased to the shared-memory image)
+      uint32_t qa0[3], qb0[3], qa1[3], qb1[3];
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const RowMma m0 = prog.mma[T0.first_mma + t];
+        const RowMma m1 = prog.mma[T1.first_mma + t];
+        qa0[t] = m0.a_lo; qb0[t] = m0.b_lo + wb;
+        qa1[t] = m1.a_lo; qb1[t] = m1.b_lo + wb;
+      }
+      const uint32_t grp0 = prog.mma[T0.first_mma].grp16, grp1 = prog.mma[T1.first_mma].grp16;
+      const bool fast1 = (a.n_sub >= 2) && T1.rows3 && (T1.ring == 0);
       int n_base = 0;  // output rows of this pipeline before the current segment
       int row_no = 0;
       RowSeg sg;
@@ -195,25 +250,35 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           // output rows this input row feeds through the three vertical taps: group g <-> output row yi - 1 + g
           const int gl = max(sg.r0 - (yi - 1), 0), gh = min(sg.r1 - 1 - (yi - 1), 2);
           const int n_g0 = n_base + (yi - 1 - sg.r0);  // running index of group 0's output row
+          const int slot0 = n_g0 & smask;
           // An output row is initialised by its first input row: yi + 1 always is, row 0 also by input row 0. Its
-          // ring slot must have been drained (by the row that used it S rows ago).
+          // ring slot must have been drained (by the row that used it S rows ago). Both barrier polls of the row
+          // (that slot, the first A slot) are issued before the run construction so that their latencies overlap it.
+          const int n_init = n_g0 + ((yi == 0 && gl <= 1) ? 1 : 2);  // first output row this input row initialises
+          const bool has_init = (gh == 2) || (yi == 0 && gh >= 1);
+          const uint32_t init_par = (static_cast<uint32_t>(n_init >> sshift) & 1u) ^ 1u;
+          const uint32_t ok_ring = has_init ? mbar_try_wait(&tempty[n_init & smask], init_par) : 1u;
+          const uint32_t ok_a0 = mbar_try_wait(&afull[ar.idx], ar.phase);
           // runs: ro = every MMA but the initialising one (split at the ring wrap), rf = the initialising MMA (split
           // also where overwrite / accumulate changes)
           uint32_t ro_slot[3], ro_ng[3], ro_g0[3], rf_slot[3], rf_ng[3], rf_g0[3], rf_acc[3];
           int n_ro = 0, n_rf = 0;
-          {
+          if (gl == 0 && gh == 2 && slot0 + 2 <= smask && yi != 0) {
+            // the common row: three output rows, no ring wrap -> one MMA per record; the initialising one is split
+            // into [rows above and same: accumulate] and [row below: overwrite]
+            n_ro = 1;
+            ro_slot[0] = static_cast<uint32_t>(slot0); ro_ng[0] = 3; ro_g0[0] = 0;
+            ro_slot[1] = ro_slot[2] = 0; ro_ng[1] = ro_ng[2] = 0; ro_g0[1] = ro_g0[2] = 0;
+            n_rf = 2;
+            rf_slot[0] = static_cast<uint32_t>(slot0); rf_ng[0] = 2; rf_g0[0] = 0; rf_acc[0] = 1;
+            rf_slot[1] = static_cast<uint32_t>(slot0 + 2); rf_ng[1] = 1; rf_g0[1] = 2; rf_acc[1] = 0;
+            rf_slot[2] = 0; rf_ng[2] = 0; rf_g0[2] = 0; rf_acc[2] = 1;
+          } else {
             // link(g): groups g and g + 1 may share an MMA -- their slots are consecutive (no ring wrap between
             // them) and, for the initialising MMA, they agree on overwrite / accumulate
             const bool init1 = (yi == 0);                              // group 1 is initialised only by input row 0
-            const bool lo0 = ((n_g0 & smask) != smask), lo1 = (((n_g0 + 1) & smask) != smask);
+            const bool lo0 = (slot0 != smask), lo1 = (((n_g0 + 1) & smask) != smask);
             const bool lf0 = lo0 && !init1, lf1 = lo1 && init1;        // inits: g0 never, g1 iff row 0, g2 always
-#pragma unroll
-            for (int g = 0; g < 3; ++g) {
-              if (g >= gl && g <= gh && (g == 2 || (g == 1 && init1))) {
-                const int n = n_g0 + g;
-                mbar_wait(&tempty[n & smask], (static_cast<uint32_t>(n >> sshift) & 1u) ^ 1u, a.err, 2);
-              }
-            }
             int g = gl;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -250,88 +315,121 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               g += (cnt > 0) ? cnt : 1;
             }
           }
+          // accumulator addresses / instruction descriptors of the runs in ring 0, of the centre row in ring 1
+          uint32_t od[3], oi[3], fd[3], fi[3];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            od[r] = d_ring0 + ro_slot[r] * aw0;
+            oi[r] = idesc0 | (((ro_ng[r] * aw0) >> 3) << 17);
+            fd[r] = d_ring0 + rf_slot[r] * aw0;
+            fi[r] = idesc0 | (((rf_ng[r] * aw0) >> 3) << 17);
+          }
           const uint32_t slot_c = static_cast<uint32_t>((n_g0 + 1) & smask);  // ring slot of the centre row
+          if (lane == 0) RTL(row_no, 8);
+          if (!ok_ring) row_wait(&tempty[n_init & smask], init_par, a.err, 2);
+          // (row 0 of an image initialises two output rows: the second slot was drained before the first, in order)
+          if (yi == 0 && gl <= 1 && gh == 2) {
+            const int n2 = n_g0 + 2;
+            row_wait(&tempty[n2 & smask], (static_cast<uint32_t>(n2 >> sshift) & 1u) ^ 1u, a.err, 2);
+          }
           tc_fence_after();
           if (lane == 0) RTL(row_no, 1);
-          bool first_sub = true;
-          for (int s = 0; s < a.n_sub; ++s) {
-            const RowSub T = prog.sub[s];
-            if (!T.rows3 && !centre) continue;
-            mbar_wait(&afull[ar.idx], ar.phase, a.err, 2);
-            tc_fence_after();
-            if (first_sub && lane == 0) RTL(row_no, 2);
-            first_sub = false;
-            if (elect_one()) {
-              const uint32_t slot16 = smem_u32(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes) >> 4;
-              const uint32_t aw = T.aw;
-              const uint32_t d0 = tmem + (T.ring ? ring1_col : ring0_col);
+          if (!ok_a0) row_wait(&afull[ar.idx], ar.phase, a.err, 2);
+          if (lane == 0) RTL(row_no, 2);
+          if (elect_one()) {
+            RTL(row_no, 9);
+            const uint32_t slot16 = smem_u32(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes) >> 4;
+            int s_begin = 0;
+            {
+              // sub-tiles 0 and 1 from registers, one pass over their taps per run of output rows (one run unless
+              // the ring wraps inside this row's three output rows). Sub-tile 0 is always the first 3x3 term of ring
+              // 0: it carries the initialising MMAs, which cover every output row of this input row.
+              {
+                const uint32_t sub16 = slot16 + (static_cast<uint32_t>(T0.off_kib) << 6);
+                const uint32_t a0 = qa0[0] + sub16, a1 = qa0[1] + sub16, a2 = qa0[2] + sub16;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                  if (r < n_rf) umma_bf16_split(fd[r], a0, T0.a_hi, qb0[0] + rf_g0[r] * grp0, T0.b_hi, fi[r], rf_acc[r]);
+                for (int r = 0; r < n_ro; ++r) {  // a runtime loop: the MMA sequences below exist once in the code
+                  const uint32_t d = (r == 0) ? od[0] : ((r == 1) ? od[1] : od[2]);
+                  const uint32_t id = (r == 0) ? oi[0] : ((r == 1) ? oi[1] : oi[2]);
+                  const uint32_t boff = ((r == 0) ? ro_g0[0] : ((r == 1) ? ro_g0[1] : ro_g0[2])) * grp0;
+                  if (T0.nk == 4)
+                    row_issue3<4>(d, id, a0, a1, a2, qb0[0] + boff, qb0[1] + boff, qb0[2] + boff, T0.a_hi, T0.b_hi, 1u);
+                  else if (T0.nk == 2)
+                    row_issue3<2>(d, id, a0, a1, a2, qb0[0] + boff, qb0[1] + boff, qb0[2] + boff, T0.a_hi, T0.b_hi, 1u);
+                  else
+                    row_issue3<1>(d, id, a0, a1, a2, qb0[0] + boff, qb0[1] + boff, qb0[2] + boff, T0.a_hi, T0.b_hi, 1u);
+                }
+                s_begin = 1;
+              }
+              if (fast1) {
+                const uint32_t sub16 = slot16 + (static_cast<uint32_t>(T1.off_kib) << 6);
+                const uint32_t a0 = qa1[0] + sub16, a1 = qa1[1] + sub16, a2 = qa1[2] + sub16;
+                for (int r = 0; r < n_ro; ++r) {
+                  const uint32_t d = (r == 0) ? od[0] : ((r == 1) ? od[1] : od[2]);
+                  const uint32_t id = (r == 0) ? oi[0] : ((r == 1) ? oi[1] : oi[2]);
+                  const uint32_t boff = ((r == 0) ? ro_g0[0] : ((r == 1) ? ro_g0[1] : ro_g0[2])) * grp1;
+                  if (T1.nk == 4)
+                    row_issue3<4>(d, id, a0, a1, a2, qb1[0] + boff, qb1[1] + boff, qb1[2] + boff, T1.a_hi, T1.b_hi, 0u);
+                  else if (T1.nk == 2)
+                    row_issue3<2>(d, id, a0, a1, a2, qb1[0] + boff, qb1[1] + boff, qb1[2] + boff, T1.a_hi, T1.b_hi, 0u);
+                  else
+                    row_issue3<1>(d, id, a0, a1, a2, qb1[0] + boff, qb1[1] + boff, qb1[2] + boff, T1.a_hi, T1.b_hi, 0u);
+                }
+                s_begin = 2;
+              }
+            }
+            for (int s = s_begin; s < a.n_sub; ++s) {
+              const RowSub T = (s == 0) ? T0 : ((s == 1) ? T1 : prog.sub[s]);
+              if (!T.rows3 && !centre) continue;
+              const uint32_t sub16 = slot16 + (static_cast<uint32_t>(T.off_kib) << 6);
               const uint32_t a_hi = T.a_hi, b_hi = T.b_hi;
               const int i_end = T.first_mma + T.n_mma;
+              const int nk = T.nk;
               if (T.rows3) {
-                uint32_t fd[3], fi[3];
+                for (int i = T.first_mma; i < i_end; ++i) {
+                  // one record per horizontal tap: nk MMAs (K = 16 slices) per run
+                  const uint4 q = *reinterpret_cast<const uint4*>(&prog.mma[i]);
+                  const uint32_t a_lo = q.x + sub16, b_lo = q.y + wb;
+                  int k0 = 0;
+                  if (q.w & ROWTAP_RING_FIRST) {
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                  fd[r] = d0 + rf_slot[r] * aw;
-                  fi[r] = idesc0 | (((rf_ng[r] * aw) >> 3) << 17);
-                }
-                if (n_ro == 1) {
-                  // no ring wrap inside this row (the common case): one MMA per record
-                  const uint32_t od = d0 + ro_slot[0] * aw;
-                  const uint32_t oi = idesc0 | (((ro_ng[0] * aw) >> 3) << 17);
-                  const uint32_t g0 = ro_g0[0];
-                  for (int i = T.first_mma; i < i_end; ++i) {
-                    const uint4 q = *reinterpret_cast<const uint4*>(&prog.mma[i]);
-                    const uint32_t a_lo = q.x + slot16, b_lo = q.y + wb;
-                    if (q.w & ROWTAP_RING_FIRST) {
-#pragma unroll
-                      for (int r = 0; r < 3; ++r)
-                        if (r < n_rf) umma_bf16_split(fd[r], a_lo, a_hi, b_lo + rf_g0[r] * q.z, b_hi, fi[r], rf_acc[r]);
-                    } else {
-                      umma_bf16_split(od, a_lo, a_hi, b_lo + g0 * q.z, b_hi, oi, 1u);
-                    }
+                    for (int r = 0; r < 3; ++r)
+                      if (r < n_rf) umma_bf16_split(fd[r], a_lo, a_hi, b_lo + rf_g0[r] * q.z, b_hi, fi[r], rf_acc[r]);
+                    k0 = 1;
                   }
-                } else {
-                  uint32_t od[3], oi[3];
+                  for (int kk = k0; kk < nk; ++kk) {
 #pragma unroll
-                  for (int r = 0; r < 3; ++r) {
-                    od[r] = d0 + ro_slot[r] * aw;
-                    oi[r] = idesc0 | (((ro_ng[r] * aw) >> 3) << 17);
-                  }
-                  for (int i = T.first_mma; i < i_end; ++i) {
-                    const uint4 q = *reinterpret_cast<const uint4*>(&prog.mma[i]);
-                    const uint32_t a_lo = q.x + slot16, b_lo = q.y + wb;
-                    if (q.w & ROWTAP_RING_FIRST) {
-#pragma unroll
-                      for (int r = 0; r < 3; ++r)
-                        if (r < n_rf) umma_bf16_split(fd[r], a_lo, a_hi, b_lo + rf_g0[r] * q.z, b_hi, fi[r], rf_acc[r]);
-                    } else {
-#pragma unroll
-                      for (int r = 0; r < 3; ++r)
-                        if (r < n_ro) umma_bf16_split(od[r], a_lo, a_hi, b_lo + ro_g0[r] * q.z, b_hi, oi[r], 1u);
-                    }
+                    for (int r = 0; r < 3; ++r)
+                      if (r < n_ro)
+                        umma_bf16_split(od[r], a_lo + 2u * kk, a_hi, b_lo + ro_g0[r] * q.z + 2u * kk, b_hi, oi[r], 1u);
                   }
                 }
               } else {
-                // 1x1 term: only the centre row; the first record of the ring's first tap overwrites
-                const uint32_t dc = d0 + slot_c * aw;
-                const uint32_t ic = idesc0 | ((aw >> 3) << 17);
+                // 1x1 term: only the centre row; the first K slice of the ring's first tap overwrites
+                const uint32_t dc = (T.ring ? d_ring1 + slot_c * aw1 : d_ring0 + slot_c * aw0);
+                const uint32_t ic = idesc0 | ((static_cast<uint32_t>(T.aw) >> 3) << 17);
                 for (int i = T.first_mma; i < i_end; ++i) {
                   const uint4 q = *reinterpret_cast<const uint4*>(&prog.mma[i]);
-                  umma_bf16_split(dc, q.x + slot16, a_hi, q.y + wb, b_hi, ic, (q.w & ROWTAP_RING_FIRST) ? 0u : 1u);
+                  for (int kk = 0; kk < nk; ++kk)
+                    umma_bf16_split(dc, q.x + sub16 + 2u * kk, a_hi, q.y + wb + 2u * kk, b_hi, ic,
+                                    ((q.w & ROWTAP_RING_FIRST) && kk == 0) ? 0u : 1u);
                 }
               }
-              umma_commit(&aempty[ar.idx]);
             }
-            __syncwarp();
-            ar.advance(a.a_slots);
-          }
-          if (lane == 0) RTL(row_no, 3);
-          // output rows completed by this input row: the one above it; at the bottom of the image also its own
-          if (elect_one()) {
-            if (yi - 1 >= sg.r0) umma_commit(&tfull[n_g0 & smask]);
+            RTL(row_no, 10);
+            // one commit frees the row slot, one (two at the bottom of an image) publishes the completed output rows:
+            // the row above this input row, at the bottom of the image also its own
+            umma_commit(&aempty[ar.idx]);
+            RTL(row_no, 11);
+            if (yi - 1 >= sg.r0) umma_commit(&tfull[slot0]);
             if (yi == a.H - 1 && sg.r1 == a.H) umma_commit(&tfull[(n_g0 + 1) & smask]);
           }
           __syncwarp();
+          ar.advance(a.a_slots);
+          if (lane == 0) RTL(row_no, 3);
+          if (lane == 0) RTL(row_no, 12);
         }
         n_base += sg.r1 - sg.r0;
       }
@@ -365,7 +463,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         if (n_step == 2 && (n & 1) != eg) continue;
         const int slot = n & smask;
         if (q == 0 && lane == 0) RTL(n, 5);
-        mbar_wait(&tfull[slot], static_cast<uint32_t>(n >> sshift) & 1u, a.err, 3);
+        row_wait(&tfull[slot], static_cast<uint32_t>(n >> sshift) & 1u, a.err, 3);
         tc_fence_after();
         if (q == 0 && lane == 0) RTL(n, 6);
         const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + ring0_col +
@@ -392,6 +490,11 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   if (warp == kRowIssuerWarp0) {
     tc_fence_after();
     tmem_dealloc(tmem, static_cast<uint32_t>(a.tmem_cols));
+  }
+  if (a.cta_times && threadIdx.x == 0 && blockIdx.x < 256) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.cta_times[2 * blockIdx.x + 1] = static_cast<long long>(t);
   }
 }
 

@@ -33,8 +33,8 @@ constexpr int kRowPipes = 2;           // independent pipelines per CTA (own til
 constexpr int kRowEpiWarps = 8;        // two groups of four: one per pipeline, or alternating rows of a single pipeline
 constexpr int kRowThreads = (kRowEpiWarps + 2 * kRowPipes) * 32;  // + one issuer and one producer warp per pipeline
 constexpr int kRowMaxSub = 8;
-constexpr int kRowMaxMma = 80;         // MMA records per input row (sub-tiles x horizontal taps x K slices)
-constexpr int kRowMaxASlots = 12;      // per pipeline
+constexpr int kRowMaxMma = 24;         // tap records per input row (sub-tiles x horizontal taps)
+constexpr int kRowMaxASlots = 8;       // row slots per pipeline
 constexpr int kRowMaxRing = 16;        // per pipeline
 
 enum : uint32_t {
@@ -42,9 +42,9 @@ enum : uint32_t {
   ROWTAP_RING_FIRST = 2  // first MMA of its accumulator ring in an input row: the one that initialises new output rows
 };
 
-struct __align__(16) RowMma {  // one tcgen05.mma of an input row (a 3x3 term issues it once per run of output rows)
-  uint32_t a_lo;         // A descriptor lower half relative to the slot: (dx * pixel_bytes + 32 k) >> 4 | LBO field
-  uint32_t b_lo;         // weight tile offset inside the launch's weight image (+ 32 k) >> 4
+struct __align__(16) RowMma {  // one horizontal tap of a sub-tile: nk tcgen05.mma (K = 16 slices) per run of output rows
+  uint32_t a_lo;         // A descriptor lower half relative to the slot: (dx * pixel_bytes) >> 4 | LBO field
+  uint32_t b_lo;         // weight tile offset inside the launch's weight image >> 4
   uint32_t grp16;        // bytes of one vertical tap's rows of the weight tile >> 4 (aw * pixel_bytes / 16)
   uint32_t flags;        // ROWTAP_*
 };
@@ -53,15 +53,16 @@ struct RowSub {          // one A sub-tile = (source tensor, channel block) of o
   int32_t c;             // first channel (coordinate 0 of the TMA box)
   uint32_t bytes;        // box bytes = 130 * pixel_bytes
   uint32_t a_hi, b_hi;   // descriptor upper halves (SBO = 8 rows, version, swizzle mode)
-  uint16_t ring;         // accumulator ring of this term (0 / 1)
-  uint16_t aw;           // accumulator columns per output row in that ring
+  uint8_t ring;          // accumulator ring of this term (0 / 1)
+  uint8_t aw;            // accumulator columns per output row in that ring (<= 64)
   uint8_t src;           // tensor map 0 / 1
   uint8_t rows3;         // 1: 3x3 term (reads halo rows), 0: 1x1 term (centre rows only)
   uint8_t first_mma;     // index into RowProg::mma
-  uint8_t n_mma;         // records of this sub-tile: horizontal taps x K slices
-  uint8_t pad[4];
+  uint8_t n_mma;         // records of this sub-tile: its horizontal taps (3 or 1)
+  uint8_t nk;            // K = 16 slices per tap
+  uint8_t off_kib;       // offset of this sub-tile inside a row slot, KiB
 };
-static_assert(sizeof(RowSub) == 28, "RowSub layout");
+static_assert(sizeof(RowSub) == 24, "RowSub layout");
 
 struct RowProg {
   RowSub sub[kRowMaxSub];
@@ -75,13 +76,15 @@ struct RowArgs {
   int W, H, B;             // pixel grid (W a multiple of 128)
   int tiles_x;             // W / 128
   int n_pipes;             // 1 or 2 pipelines per CTA
-  int a_slots, a_slot_bytes;   // A slots per pipeline
+  int a_slots, a_slot_bytes;   // row slots per pipeline (one slot = every sub-tile of one input row), bytes of one
+  uint32_t row_bytes3, row_bytes_all;  // TMA bytes of a halo row (3x3 terms only) / of a centre row
   int ring_slots;          // S: output rows in flight per ring and pipeline (a power of two >= 4)
   int ring_aw[2];          // accumulator columns per output row of ring 0 / 1 (0: no second ring)
   int tmem_cols;           // allocation (power of two >= ring columns of all pipelines)
   int n_acc;               // channels the epilogue produces per pixel (N of the epilogue)
   int store_sbc;           // EPI_STD: channels per TMA-store sub-box (0: per-thread stores)
-  long long* timeline;     // debug (DRS_V2_TIMELINE): CTA 0 stamps 8 clock values per row into this buffer, else null
+  long long* timeline;     // debug (DRS_V2_TIMELINE & 1): pipeline 0 of CTA 0 stamps 16 clock values per row, else null
+  long long* cta_times;    // debug (DRS_V2_TIMELINE & 8): [2 i] / [2 i + 1] = globaltimer at entry / exit of CTA i
   int* err;
   EpiArgs epi;
 };

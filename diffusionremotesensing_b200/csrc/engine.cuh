@@ -111,7 +111,8 @@ struct GemmSpec {
     RowProg prog;
     int n_sub = 0;
     uint32_t w_off = 0, w_bytes = 0;   // weight image inside the model's weight blob
-    int a_slot_bytes = 0;
+    int a_slot_bytes = 0;              // one row slot: every sub-tile of an input row
+    uint32_t row_bytes3 = 0, row_bytes_all = 0;
     int n_pipes = 1;                   // pipelines per CTA
     int ring_slots = 0;                // S per pipeline
     int ring_aw[2] = {0, 0};           // accumulator columns per output row of ring 0 / 1

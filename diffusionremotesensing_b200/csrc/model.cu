@@ -281,6 +281,7 @@ struct Builder {
     for (const ConvTerm& t : terms) {
       if (t.kind != CONV_3x3 && t.kind != CONV_1x1) return;
       if (t.col_slot < 0 || t.col_slot > 1) return;
+      if (t.kind == CONV_3x3 && t.col_slot != 0) return;  // the second ring only takes 1x1 terms (fused shortcut)
       const int aw = g.n_sub * static_cast<int>(t.stack.size());
       if (ring_aw[t.col_slot] && ring_aw[t.col_slot] != aw) return;
       ring_aw[t.col_slot] = aw;
@@ -298,6 +299,7 @@ struct Builder {
     while (2 * S <= kRowMaxRing && 2 * S * cols_per_slot * n_pipes <= 512) S *= 2;
     memset(&r.prog, 0, sizeof(r.prog));
     int n_sub = 0, n_mma = 0, max_pix = 0;
+    uint32_t row_slot = 0, bytes3 = 0, bytes1 = 0;   // row-slot layout: every sub-tile of one input row, 1 KiB aligned
     size_t image = 0;
     bool ring_seen[2] = {false, false};
     // pass 1: counts
@@ -305,7 +307,7 @@ struct Builder {
       const int ck = g.src_ck[t.src];
       const int taps = (t.kind == CONV_3x3) ? 3 : 1;
       n_sub += t.C / ck;
-      n_mma += taps * (t.C / ck) * (ck / 16);
+      n_mma += taps * (t.C / ck);
     }
     if (n_sub > kRowMaxSub || n_mma > kRowMaxMma) return;
     n_sub = n_mma = 0;
@@ -326,21 +328,25 @@ struct Builder {
         sub.bytes = static_cast<uint32_t>((kRowTile + 2) * pix);
         sub.a_hi = umma_desc_hi(pix, 8 * pix);
         sub.b_hi = umma_desc_hi(pix, 8 * pix);
-        sub.ring = static_cast<uint16_t>(t.col_slot);
-        sub.aw = static_cast<uint16_t>(aw);
+        sub.ring = static_cast<uint8_t>(t.col_slot);
+        sub.aw = static_cast<uint8_t>(aw);
+        sub.off_kib = static_cast<uint8_t>(row_slot >> 10);
+        row_slot += (sub.bytes + 1023u) & ~1023u;
+        (three ? bytes3 : bytes1) += sub.bytes;
         sub.src = static_cast<uint8_t>(t.src);
         sub.rows3 = three ? 1 : 0;
         sub.first_mma = static_cast<uint8_t>(n_mma);
-        sub.n_mma = static_cast<uint8_t>((three ? 3 : 1) * (ck / 16));
+        sub.n_mma = static_cast<uint8_t>(three ? 3 : 1);
+        sub.nk = static_cast<uint8_t>(ck / 16);
         for (int dx = 0; dx < (three ? 3 : 1); ++dx) {
           // the box starts one pixel left of x0: horizontal tap dx reads from pixel dx on (a 1x1 term from pixel 1)
           const uint32_t a_off16 = static_cast<uint32_t>(((three ? dx : 1) * pix) >> 4);
-          for (int k = 0; k < ck / 16; ++k) {
+          {
             RowMma& mm = r.prog.mma[n_mma++];
-            mm.a_lo = 0x10000u | (a_off16 + 2u * k);
-            mm.b_lo = static_cast<uint32_t>(image >> 4) + 2u * k;
+            mm.a_lo = 0x10000u | a_off16;
+            mm.b_lo = static_cast<uint32_t>(image >> 4);
             mm.grp16 = static_cast<uint32_t>((aw * pix) >> 4);
-            mm.flags = (three ? ROWTAP_3ROWS : 0u) | ((!ring_seen[t.col_slot] && k == 0) ? ROWTAP_RING_FIRST : 0u);
+            mm.flags = (three ? ROWTAP_3ROWS : 0u) | (ring_seen[t.col_slot] ? 0u : ROWTAP_RING_FIRST);
           }
           ring_seen[t.col_slot] = true;
           const size_t tile_bytes = (static_cast<size_t>(n_grp) * aw * pix + 1023) & ~static_cast<size_t>(1023);
@@ -369,14 +375,18 @@ struct Builder {
     r.n_sub = n_sub;
     r.w_off = static_cast<uint32_t>(w_off);
     r.w_bytes = static_cast<uint32_t>(image);
-    r.a_slot_bytes = ((kRowTile + 2) * max_pix + 1023) & ~1023;
+    r.a_slot_bytes = static_cast<int>(row_slot);
+    r.row_bytes3 = bytes3;
+    r.row_bytes_all = bytes3 + bytes1;
     r.ring_slots = S;
     r.n_pipes = n_pipes;
     r.ring_aw[0] = ring_aw[0];
     r.ring_aw[1] = ring_aw[1];
     r.col2 = ring_aw[1] ? S * ring_aw[0] : g.col2;
-    // resident weights + at least max(3, 2 sub-tiles) A slots per pipeline + the store staging must fit
-    const size_t need = image + static_cast<size_t>(n_pipes) * std::max(3, 2 * n_sub) * r.a_slot_bytes + kStageBytes;
+    // resident weights + at least three row slots (one pipeline; the plan takes two when they fit) + the store
+    // staging must fit
+    const size_t need = image + static_cast<size_t>(3) * r.a_slot_bytes +
+                        (g.epi_kind == EPI_STD ? kStageBytes : 0);
     if (need > 200 * 1024) {
       m->wblob.resize(w_off);
       return;

@@ -428,11 +428,12 @@ static int bind_launch_row(DrsPlan* p, const void* src0, const void* src1, int g
   a.B = p->nb;
   a.tiles_x = gridW / kRowTile;
   a.a_slot_bytes = r.a_slot_bytes;
+  a.row_bytes3 = r.row_bytes3;
+  a.row_bytes_all = r.row_bytes_all;
   // two pipelines only when each still gets a dozen rows (every range re-reads two halo rows)
   static const char* const pipes_env = getenv("DRS_ROW_PIPES");
-  const int n_pipes = pipes_env ? std::max(1, std::min(r.n_pipes, atoi(pipes_env)))
-                                : ((tiles >= 24LL * sms) ? r.n_pipes : 1);
-  a.n_pipes = n_pipes;
+  int n_pipes = pipes_env ? std::max(1, std::min(r.n_pipes, atoi(pipes_env)))
+                          : ((tiles >= 24LL * sms) ? r.n_pipes : 1);
   a.ring_slots = r.ring_slots;
   a.ring_aw[0] = r.ring_aw[0];
   a.ring_aw[1] = r.ring_aw[1];
@@ -442,8 +443,9 @@ static int bind_launch_row(DrsPlan* p, const void* src0, const void* src1, int g
   {
     static const int timeline = getenv("DRS_V2_TIMELINE") ? atoi(getenv("DRS_V2_TIMELINE")) : 0;
     static const char* const tl_layer = getenv("DRS_V2_TIMELINE_LAYER");
-    a.timeline = ((timeline & 1) && (!tl_layer || g.name.find(tl_layer) != std::string::npos))
-                     ? conv_gemm2_timeline_dev() : nullptr;
+    const bool mine = (!tl_layer || g.name.find(tl_layer) != std::string::npos);
+    a.timeline = ((timeline & 1) && mine) ? conv_gemm2_timeline_dev() : nullptr;
+    a.cta_times = ((timeline & 8) && mine) ? conv_gemm2_timeline_dev() : nullptr;
   }
   a.epi = L->args.epi;
   a.epi.col2 = r.col2;
@@ -452,8 +454,13 @@ static int bind_launch_row(DrsPlan* p, const void* src0, const void* src1, int g
   const int stage_bytes = stage ? kStageBytes : 0;
   const int w_pad = static_cast<int>((r.w_bytes + 1023u) & ~1023u);
   const int budget = 227 * 1024 - 16 * 1024 - w_pad - stage_bytes;
-  const int slots = std::min(kRowMaxASlots, budget / r.a_slot_bytes / n_pipes);  // per pipeline
-  if (slots < std::max(3, 2 * r.n_sub)) return DRS_OK;
+  int slots = std::min(kRowMaxASlots, budget / r.a_slot_bytes / n_pipes);  // per pipeline
+  if (n_pipes == 2 && slots < 3) {
+    n_pipes = 1;  // shared memory holds the A ring of one pipeline only
+    slots = std::min(kRowMaxASlots, budget / r.a_slot_bytes);
+  }
+  if (slots < 3) return DRS_OK;
+  a.n_pipes = n_pipes;
   a.a_slots = slots;
   const void* srcs[2] = {src0, src1};
   CUtensorMap maps[2];

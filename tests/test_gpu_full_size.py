@@ -1,8 +1,10 @@
 """Size-independent properties checked at BASELINE.json's full size (cfg 2: superres x2, LR 128 -> 256, n = 16), where
 the CPU oracle would need minutes per evaluation:
 
-  * a sample's result does not depend on what else is in the batch: the first two samples of the 16-image evaluation
-    are bit-identical to a 2-image evaluation (different plan, different tile -> CTA assignment, same arithmetic);
+  * a sample's result does not depend on what else is in the batch: the first 14 samples of the 16-image evaluation
+    are bit-identical to a 14-image evaluation (different plan, different tile / row-range -> CTA assignment, same
+    arithmetic), and within rounding noise of a 2-image evaluation, which is small enough to take the tile kernel
+    where the 16-image plan takes the row-streaming kernel (another fp32 accumulation order);
   * every kernel path (CTA pair on / off / everywhere, staged or per-thread stores, solo drain, programmatic dependent
     launch, gate branch on a side stream) produces bit-identical eps and a bit-identical 3-step trajectory.
 """
@@ -29,9 +31,11 @@ def test_batch_independence_at_full_size(cuda_device):
     t = torch.full((n,), 700, device=cuda_device)
     with torch.no_grad():
         full = m(x, t, lr, 2).clone()
-        part = m(x[:2].contiguous(), t[:2], lr, 2).clone()
+        part = m(x[:14].contiguous(), t[:14], lr, 2).clone()
+        two = m(x[:2].contiguous(), t[:2], lr, 2).clone()
     assert torch.isfinite(full).all()
-    assert torch.equal(full[:2], part), "a sample's eps changed with the batch it was evaluated in"
+    assert torch.equal(full[:14], part), "a sample's eps changed with the batch it was evaluated in"
+    assert T.max_rel_err(two, full[:2]) <= 2e-3, "tile-kernel and row-kernel evaluations of one sample disagree"
 
 
 def digest(env):
