@@ -24,7 +24,7 @@ its own GPU (weak scaling, no data-path collective).
              the aggregation blend (cfg-5 shape, 961 patches -> 3 x 4096 x 4096) -- algorithmic bytes / CUDA-event
              time on a flushed L2 / MEASURED_PEAKS.json hbm_gbs
   aggregation  cfg 5 as a STRONG-scaling leg: the 961 overlapping 128 -> 256 patches of an LR 2048 x 2048 scene, block
-             partitioned over the N ranks, sampled for min(K, 50) reverse steps, gathered to rank 0 (NCCL) and blended
+             partitioned over the N ranks, sampled for 50 reverse steps per patch, gathered to rank 0 (NCCL) and blended
              there; seconds = max over ranks of the whole thing (gather and blend inside the timed region)
   cpu_baseline  the reference algorithm (oracle port: the same torch CPU ops the reference's modules call) timed on
              this box's host cores on a bounded sample of the same workload
@@ -234,8 +234,12 @@ def aggregation_leg(model, dev, k_steps, rank, world, roofline):
     lo, hi = blocks[rank]
     n_batches = max(1, -(-(hi - lo) // agg.patch_batch))
     size = -(-(hi - lo) // n_batches)
-    # warm-up: one batch of this rank's batch size builds its plan, time table and CUDA graphs
-    agg.sample_patches(range(lo, min(hi, lo + size)), private_rng=True)
+    # warm-up: one batch of this rank's batch size builds its plan, time table and CUDA graphs; one small gather opens
+    # the NCCL point-to-point connections to rank 0 (hundreds of milliseconds on first use)
+    warm = agg.sample_patches(range(lo, min(hi, lo + size)), private_rng=True)
+    if world > 1:
+        gather_blocks(warm[:1], [1] * world, dst=0)
+    del warm
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -244,6 +248,10 @@ def aggregation_leg(model, dev, k_steps, rank, world, roofline):
     local = agg.sample_patches(range(lo, hi), private_rng=True)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()      # so that gather_ms is the transfer, not the wait for the slowest rank (that is in `seconds`)
+        torch.cuda.synchronize()
+    t1b = time.perf_counter()
     patches = gather_blocks(local, counts, dst=0) if world > 1 else local
     torch.cuda.synchronize()
     t2 = time.perf_counter()
@@ -266,7 +274,7 @@ def aggregation_leg(model, dev, k_steps, rank, world, roofline):
     res = {"workload": f"cfg 5: LR {side}x{side} scene -> {n} patches {P}->{P * k}, stride {stride}, "
                        f"{k_steps} reverse steps per patch", "scaling": "strong", "patches": n, "steps": k_steps,
            "n_gpus": world, "patches_per_rank": counts, "patch_batch": size, "seconds": total,
-           "sample_seconds_max_rank": sample_s, "gather_ms": (t2 - t1) * 1e3, "blend_ms": blend_ms,
+           "sample_seconds_max_rank": sample_s, "gather_ms": (t2 - t1b) * 1e3, "blend_ms": blend_ms,
            "image_steps_per_sec": n * k_steps / total,
            "note": "seconds = first patch to blended scene on rank 0, max over ranks; gather_ms / blend_ms are rank 0's"}
     if rank == 0 and roofline is not None:
@@ -486,7 +494,7 @@ def run_ours(args):
     # ---- cfg 5: aggregation sampling of an LR 2048 x 2048 scene, patch list sharded over the ranks (strong scaling) ----
     aggregation = None
     if not args.no_aggregation:
-        aggregation = aggregation_leg(model, dev, min(K, 50), rank, world, roofline)
+        aggregation = aggregation_leg(model, dev, 50, rank, world, roofline)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------------
     cpu = None

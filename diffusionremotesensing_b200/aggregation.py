@@ -44,21 +44,31 @@ def partition_blocks(n_items: int, world_size: int) -> List[Tuple[int, int]]:
 
 
 def gather_blocks(local: torch.Tensor, counts: Sequence[int], dst: int = 0, group=None) -> Optional[torch.Tensor]:
-    """Gathers per-rank blocks [counts[r], ...] to rank `dst` in rank order (the one collective of the path)."""
+    """Gathers per-rank blocks [counts[r], ...] to rank `dst` in rank order (the one collective of the path).
+    Point-to-point: every rank sends its block once, `dst` receives each block straight into its slice of the result
+    (no padding to the largest block, no staging copies); empty blocks are skipped on both sides."""
     import torch.distributed as dist
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
-    cap = max(counts)
-    padded = local
-    if local.shape[0] != cap:
-        padded = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        padded[: local.shape[0]] = local
-    padded = padded.contiguous()
-    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
-    dist.gather(padded, bufs, dst=dst, group=group)
+    local = local.contiguous()
     if rank != dst:
+        if counts[rank] > 0:
+            dist.send(local, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
         return None
-    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    out = torch.empty((sum(counts),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    out[offs[dst]:offs[dst + 1]] = local
+    reqs = []
+    for r in range(world):
+        if r == dst or counts[r] == 0:
+            continue
+        src = dist.get_global_rank(group, r) if group is not None else r
+        reqs.append(dist.irecv(out[offs[r]:offs[r + 1]], src=src, group=group))
+    for q in reqs:
+        q.wait()
+    return out
 
 
 def blend_patches(patches: torch.Tensor, infos: Sequence[Tuple[int, int, int, int]], weight2d: torch.Tensor,

@@ -93,6 +93,187 @@ __device__ __forceinline__ void row_issue3(uint32_t d, uint32_t idesc, uint32_t 
   for (int k = 0; k < NK; ++k) umma_bf16_split(d, a2 + 2u * k, a_hi, b2 + 2u * k, b_hi, idesc, 1u);
 }
 
+// What one input row does to the accumulator ring, worked out once per row: at most three "runs" of consecutive ring
+// slots for the ordinary MMAs (ro: split only where the ring wraps) and for the row's initialising MMA (rf: split also
+// where overwrite / accumulate changes), with their TMEM addresses and instruction descriptors.
+struct RowPlan {
+  uint32_t od[3], oi[3], ro_g0[3];
+  uint32_t fd[3], fi[3], rf_g0[3], rf_acc[3];
+  int n_ro, n_rf;
+  uint32_t slot0, slot_c;     // ring slots of the output row above this input row / of its own (centre) row
+  int n_init;                 // running index of the first output row this input row initialises
+  uint32_t init_par;          // parity of that slot's "drained" barrier
+  bool has_init, init_two;    // initialises one row / two rows (input row 0 of an image)
+  bool centre, commit_prev, commit_own;
+};
+
+__device__ __forceinline__ void row_plan(RowPlan& P, int yi, const RowSeg& sg, int n_base, int H, int smask, int sshift,
+                                         uint32_t aw0, uint32_t d_ring0, uint32_t idesc0) {
+  P.centre = (yi >= sg.r0) && (yi < sg.r1);
+  // output rows this input row feeds through the three vertical taps: group g <-> output row yi - 1 + g
+  const int gl = max(sg.r0 - (yi - 1), 0), gh = min(sg.r1 - 1 - (yi - 1), 2);
+  const int n_g0 = n_base + (yi - 1 - sg.r0);  // running index of group 0's output row
+  const int slot0 = n_g0 & smask;
+  P.slot0 = static_cast<uint32_t>(slot0);
+  P.slot_c = static_cast<uint32_t>((n_g0 + 1) & smask);
+  // An output row is initialised by its first input row: yi + 1 always is, row 0 also by input row 0.
+  P.n_init = n_g0 + ((yi == 0 && gl <= 1) ? 1 : 2);
+  P.has_init = (gh == 2) || (yi == 0 && gh >= 1);
+  P.init_two = (yi == 0 && gl <= 1 && gh == 2);
+  P.init_par = (static_cast<uint32_t>(P.n_init >> sshift) & 1u) ^ 1u;
+  P.commit_prev = (yi - 1 >= sg.r0);
+  P.commit_own = (yi == H - 1 && sg.r1 == H);
+  uint32_t ro_slot[3], ro_ng[3], rf_slot[3], rf_ng[3];
+  if (gl == 0 && gh == 2 && slot0 + 2 <= smask && yi != 0) {
+    // the common row: three output rows, no ring wrap -> one MMA per tap and K slice; the initialising one is split
+    // into [rows above and same: accumulate] and [row below: overwrite]
+    P.n_ro = 1;
+    ro_slot[0] = static_cast<uint32_t>(slot0); ro_ng[0] = 3; P.ro_g0[0] = 0;
+    ro_slot[1] = ro_slot[2] = 0; ro_ng[1] = ro_ng[2] = 0; P.ro_g0[1] = P.ro_g0[2] = 0;
+    P.n_rf = 2;
+    rf_slot[0] = static_cast<uint32_t>(slot0); rf_ng[0] = 2; P.rf_g0[0] = 0; P.rf_acc[0] = 1;
+    rf_slot[1] = static_cast<uint32_t>(slot0 + 2); rf_ng[1] = 1; P.rf_g0[1] = 2; P.rf_acc[1] = 0;
+    rf_slot[2] = 0; rf_ng[2] = 0; P.rf_g0[2] = 0; P.rf_acc[2] = 1;
+  } else {
+    // link(g): groups g and g + 1 may share an MMA -- their slots are consecutive (no ring wrap between them) and,
+    // for the initialising MMA, they agree on overwrite / accumulate
+    const bool init1 = (yi == 0);                              // group 1 is initialised only by input row 0
+    const bool lo0 = (slot0 != smask), lo1 = (((n_g0 + 1) & smask) != smask);
+    const bool lf0 = lo0 && !init1, lf1 = lo1 && init1;        // inits: g0 never, g1 iff row 0, g2 always
+    P.n_ro = P.n_rf = 0;
+    int g = gl;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int cnt = 0;
+      if (g <= gh) {
+        cnt = 1;
+        if (g + 1 <= gh && (g == 0 ? lo0 : lo1)) {
+          cnt = 2;
+          if (g == 0 && gh == 2 && lo1) cnt = 3;
+        }
+        P.n_ro = r + 1;
+      }
+      P.ro_g0[r] = static_cast<uint32_t>(g);
+      ro_ng[r] = static_cast<uint32_t>(cnt);
+      ro_slot[r] = static_cast<uint32_t>((n_g0 + g) & smask);
+      g += (cnt > 0) ? cnt : 1;
+    }
+    g = gl;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int cnt = 0;
+      if (g <= gh) {
+        cnt = 1;
+        if (g + 1 <= gh && (g == 0 ? lf0 : lf1)) {
+          cnt = 2;
+          if (g == 0 && gh == 2 && lf1) cnt = 3;
+        }
+        P.n_rf = r + 1;
+      }
+      P.rf_g0[r] = static_cast<uint32_t>(g);
+      rf_ng[r] = static_cast<uint32_t>(cnt);
+      rf_slot[r] = static_cast<uint32_t>((n_g0 + g) & smask);
+      P.rf_acc[r] = (g == 2 || (g == 1 && init1)) ? 0u : 1u;
+      g += (cnt > 0) ? cnt : 1;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    P.od[r] = d_ring0 + ro_slot[r] * aw0;
+    P.oi[r] = idesc0 | (((ro_ng[r] * aw0) >> 3) << 17);
+    P.fd[r] = d_ring0 + rf_slot[r] * aw0;
+    P.fi[r] = idesc0 | (((rf_ng[r] * aw0) >> 3) << 17);
+  }
+}
+
+// Register-resident program of the issuer: the first two sub-tile records and, when they are 3x3 terms, their tap
+// records (weight offsets already rebased to the shared-memory image).
+struct RowRegs {
+  RowSub T0, T1;
+  uint32_t qa0[3], qb0[3], qa1[3], qb1[3];
+  uint32_t grp0, grp1;
+  bool fast1;
+  uint32_t wb, idesc0, aw0, aw1, d_ring0, d_ring1;
+};
+
+// All MMAs of one input row (one elected lane). slot16: the row slot's shared-memory address >> 4.
+__device__ __forceinline__ void row_issue(const RowProg& prog, const RowRegs& R, const RowPlan& P, uint32_t slot16,
+                                          int n_sub) {
+  int s_begin = 0;
+  {
+    // sub-tiles 0 and 1 from registers, one pass over their taps per run of output rows (one run unless the ring
+    // wraps inside this row's three output rows). Sub-tile 0 is always the first 3x3 term of ring 0: it carries the
+    // initialising MMAs, which cover every output row of this input row.
+    {
+      const uint32_t sub16 = slot16 + (static_cast<uint32_t>(R.T0.off_kib) << 6);
+      const uint32_t a0 = R.qa0[0] + sub16, a1 = R.qa0[1] + sub16, a2 = R.qa0[2] + sub16;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        if (r < P.n_rf)
+          umma_bf16_split(P.fd[r], a0, R.T0.a_hi, R.qb0[0] + P.rf_g0[r] * R.grp0, R.T0.b_hi, P.fi[r], P.rf_acc[r]);
+      for (int r = 0; r < P.n_ro; ++r) {  // a runtime loop: the MMA sequences below exist once in the code
+        const uint32_t d = (r == 0) ? P.od[0] : ((r == 1) ? P.od[1] : P.od[2]);
+        const uint32_t id = (r == 0) ? P.oi[0] : ((r == 1) ? P.oi[1] : P.oi[2]);
+        const uint32_t boff = ((r == 0) ? P.ro_g0[0] : ((r == 1) ? P.ro_g0[1] : P.ro_g0[2])) * R.grp0;
+        if (R.T0.nk == 4)
+          row_issue3<4>(d, id, a0, a1, a2, R.qb0[0] + boff, R.qb0[1] + boff, R.qb0[2] + boff, R.T0.a_hi, R.T0.b_hi, 1u);
+        else if (R.T0.nk == 2)
+          row_issue3<2>(d, id, a0, a1, a2, R.qb0[0] + boff, R.qb0[1] + boff, R.qb0[2] + boff, R.T0.a_hi, R.T0.b_hi, 1u);
+        else
+          row_issue3<1>(d, id, a0, a1, a2, R.qb0[0] + boff, R.qb0[1] + boff, R.qb0[2] + boff, R.T0.a_hi, R.T0.b_hi, 1u);
+      }
+      s_begin = 1;
+    }
+    if (R.fast1) {
+      const uint32_t sub16 = slot16 + (static_cast<uint32_t>(R.T1.off_kib) << 6);
+      const uint32_t a0 = R.qa1[0] + sub16, a1 = R.qa1[1] + sub16, a2 = R.qa1[2] + sub16;
+      for (int r = 0; r < P.n_ro; ++r) {
+        const uint32_t d = (r == 0) ? P.od[0] : ((r == 1) ? P.od[1] : P.od[2]);
+        const uint32_t id = (r == 0) ? P.oi[0] : ((r == 1) ? P.oi[1] : P.oi[2]);
+        const uint32_t boff = ((r == 0) ? P.ro_g0[0] : ((r == 1) ? P.ro_g0[1] : P.ro_g0[2])) * R.grp1;
+        if (R.T1.nk == 4)
+          row_issue3<4>(d, id, a0, a1, a2, R.qb1[0] + boff, R.qb1[1] + boff, R.qb1[2] + boff, R.T1.a_hi, R.T1.b_hi, 0u);
+        else if (R.T1.nk == 2)
+          row_issue3<2>(d, id, a0, a1, a2, R.qb1[0] + boff, R.qb1[1] + boff, R.qb1[2] + boff, R.T1.a_hi, R.T1.b_hi, 0u);
+        else
+          row_issue3<1>(d, id, a0, a1, a2, R.qb1[0] + boff, R.qb1[1] + boff, R.qb1[2] + boff, R.T1.a_hi, R.T1.b_hi, 0u);
+      }
+      s_begin = 2;
+    }
+  }
+  for (int s = s_begin; s < n_sub; ++s) {
+    const RowSub T = (s == 1) ? R.T1 : prog.sub[s];
+    if (!T.rows3 && !P.centre) continue;
+    const uint32_t sub16 = slot16 + (static_cast<uint32_t>(T.off_kib) << 6);
+    const uint32_t a_hi = T.a_hi, b_hi = T.b_hi;
+    const int i_end = T.first_mma + T.n_mma;
+    const int nk = T.nk;
+    if (T.rows3) {
+      for (int i = T.first_mma; i < i_end; ++i) {
+        // one record per horizontal tap: nk MMAs (K = 16 slices) per run
+        const uint4 q = *reinterpret_cast<const uint4*>(&prog.mma[i]);
+        const uint32_t a_lo = q.x + sub16, b_lo = q.y + R.wb;
+        for (int kk = 0; kk < nk; ++kk) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+            if (r < P.n_ro)
+              umma_bf16_split(P.od[r], a_lo + 2u * kk, a_hi, b_lo + P.ro_g0[r] * q.z + 2u * kk, b_hi, P.oi[r], 1u);
+        }
+      }
+    } else {
+      // 1x1 term: only the centre row; the first K slice of the ring's first tap overwrites
+      const uint32_t dc = (T.ring ? R.d_ring1 + P.slot_c * R.aw1 : R.d_ring0 + P.slot_c * R.aw0);
+      const uint32_t ic = R.idesc0 | ((static_cast<uint32_t>(T.aw) >> 3) << 17);
+      for (int i = T.first_mma; i < i_end; ++i) {
+        const uint4 q = *reinterpret_cast<const uint4*>(&prog.mma[i]);
+        for (int kk = 0; kk < nk; ++kk)
+          umma_bf16_split(dc, q.x + sub16 + 2u * kk, a_hi, q.y + R.wb + 2u * kk, b_hi, ic,
+                          ((q.w & ROWTAP_RING_FIRST) && kk == 0) ? 0u : 1u);
+      }
+    }
+  }
+}
+
 constexpr int kRowIssuerWarp0 = kRowEpiWarps;                 // issuer of pipeline p: kRowIssuerWarp0 + p
 constexpr int kRowProducerWarp0 = kRowEpiWarps + kRowPipes;   // producer of pipeline p
 constexpr int kRowMaxNacc = 64;  // channels per pixel the epilogue of this kernel handles
@@ -222,214 +403,82 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     if (pipe < n_pipes) {
       row_wait(&s_wready, 0, a.err, 2);
       RowRing ar{0, 0};
-      const uint32_t wb = 0x10000u | (smem_u32(w_base) >> 4);
-      const uint32_t idesc0 = umma_idesc_bf16(kRowTile, 0);
-      const uint32_t aw0 = static_cast<uint32_t>(a.ring_aw[0]), aw1 = static_cast<uint32_t>(a.ring_aw[1]);
-      const uint32_t d_ring0 = tmem + ring0_col, d_ring1 = tmem + ring1_col;
-      const RowSub T0 = prog.sub[0], T1 = prog.sub[1];  // the first two sub-tile records stay in registers
-      // ... and so do the tap records of the first two sub-tiles when they are 3x3 terms (weight offsets already
-      // rebased to the shared-memory image)
-      uint32_t qa0[3], qb0[3], qa1[3], qb1[3];
+      RowRegs R;
+      R.wb = 0x10000u | (smem_u32(w_base) >> 4);
+      R.idesc0 = umma_idesc_bf16(kRowTile, 0);
+      R.aw0 = static_cast<uint32_t>(a.ring_aw[0]);
+      R.aw1 = static_cast<uint32_t>(a.ring_aw[1]);
+      R.d_ring0 = tmem + ring0_col;
+      R.d_ring1 = tmem + ring1_col;
+      R.T0 = prog.sub[0];
+      R.T1 = prog.sub[1];
 #pragma unroll
       for (int t = 0; t < 3; ++t) {
-        const RowMma m0 = prog.mma[T0.first_mma + t];
-        const RowMma m1 = prog.mma[T1.first_mma + t];
-        qa0[t] = m0.a_lo; qb0[t] = m0.b_lo + wb;
-        qa1[t] = m1.a_lo; qb1[t] = m1.b_lo + wb;
+        const RowMma m0 = prog.mma[R.T0.first_mma + t];
+        const RowMma m1 = prog.mma[R.T1.first_mma + t];
+        R.qa0[t] = m0.a_lo; R.qb0[t] = m0.b_lo + R.wb;
+        R.qa1[t] = m1.a_lo; R.qb1[t] = m1.b_lo + R.wb;
       }
-      const uint32_t grp0 = prog.mma[T0.first_mma].grp16, grp1 = prog.mma[T1.first_mma].grp16;
-      const bool fast1 = (a.n_sub >= 2) && T1.rows3 && (T1.ring == 0);
+      R.grp0 = prog.mma[R.T0.first_mma].grp16;
+      R.grp1 = prog.mma[R.T1.first_mma].grp16;
+      R.fast1 = (a.n_sub >= 2) && R.T1.rows3 && (R.T1.ring == 0);
       int n_base = 0;  // output rows of this pipeline before the current segment
       int row_no = 0;
       RowSeg sg;
       while (walk.next(sg)) {
         const int yi_lo = max(sg.r0 - 1, 0), yi_hi = min(sg.r1, a.H - 1);
-        for (int yi = yi_lo; yi <= yi_hi; ++yi, ++row_no) {
-          const bool centre = (yi >= sg.r0) && (yi < sg.r1);
+        // TWO input rows per iteration: the barrier polls, the fence, the election and the warp re-convergence cost the
+        // issuing warp ~1300 cycles per iteration whatever it issues, more than the MMAs of a low-channel row
+        for (int yi = yi_lo; yi <= yi_hi; yi += 2, row_no += 2) {
+          const bool two = (yi + 1 <= yi_hi);
           if (lane == 0) RTL(row_no, 0);
-          // output rows this input row feeds through the three vertical taps: group g <-> output row yi - 1 + g
-          const int gl = max(sg.r0 - (yi - 1), 0), gh = min(sg.r1 - 1 - (yi - 1), 2);
-          const int n_g0 = n_base + (yi - 1 - sg.r0);  // running index of group 0's output row
-          const int slot0 = n_g0 & smask;
-          // An output row is initialised by its first input row: yi + 1 always is, row 0 also by input row 0. Its
-          // ring slot must have been drained (by the row that used it S rows ago). Both barrier polls of the row
-          // (that slot, the first A slot) are issued before the run construction so that their latencies overlap it.
-          const int n_init = n_g0 + ((yi == 0 && gl <= 1) ? 1 : 2);  // first output row this input row initialises
-          const bool has_init = (gh == 2) || (yi == 0 && gh >= 1);
-          const uint32_t init_par = (static_cast<uint32_t>(n_init >> sshift) & 1u) ^ 1u;
-          const uint32_t ok_ring = has_init ? mbar_try_wait(&tempty[n_init & smask], init_par) : 1u;
-          const uint32_t ok_a0 = mbar_try_wait(&afull[ar.idx], ar.phase);
-          // runs: ro = every MMA but the initialising one (split at the ring wrap), rf = the initialising MMA (split
-          // also where overwrite / accumulate changes)
-          uint32_t ro_slot[3], ro_ng[3], ro_g0[3], rf_slot[3], rf_ng[3], rf_g0[3], rf_acc[3];
-          int n_ro = 0, n_rf = 0;
-          if (gl == 0 && gh == 2 && slot0 + 2 <= smask && yi != 0) {
-            // the common row: three output rows, no ring wrap -> one MMA per record; the initialising one is split
-            // into [rows above and same: accumulate] and [row below: overwrite]
-            n_ro = 1;
-            ro_slot[0] = static_cast<uint32_t>(slot0); ro_ng[0] = 3; ro_g0[0] = 0;
-            ro_slot[1] = ro_slot[2] = 0; ro_ng[1] = ro_ng[2] = 0; ro_g0[1] = ro_g0[2] = 0;
-            n_rf = 2;
-            rf_slot[0] = static_cast<uint32_t>(slot0); rf_ng[0] = 2; rf_g0[0] = 0; rf_acc[0] = 1;
-            rf_slot[1] = static_cast<uint32_t>(slot0 + 2); rf_ng[1] = 1; rf_g0[1] = 2; rf_acc[1] = 0;
-            rf_slot[2] = 0; rf_ng[2] = 0; rf_g0[2] = 0; rf_acc[2] = 1;
-          } else {
-            // link(g): groups g and g + 1 may share an MMA -- their slots are consecutive (no ring wrap between
-            // them) and, for the initialising MMA, they agree on overwrite / accumulate
-            const bool init1 = (yi == 0);                              // group 1 is initialised only by input row 0
-            const bool lo0 = (slot0 != smask), lo1 = (((n_g0 + 1) & smask) != smask);
-            const bool lf0 = lo0 && !init1, lf1 = lo1 && init1;        // inits: g0 never, g1 iff row 0, g2 always
-            int g = gl;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              int cnt = 0;
-              if (g <= gh) {
-                cnt = 1;
-                if (g + 1 <= gh && (g == 0 ? lo0 : lo1)) {
-                  cnt = 2;
-                  if (g == 0 && gh == 2 && lo1) cnt = 3;
-                }
-                n_ro = r + 1;
-              }
-              ro_g0[r] = static_cast<uint32_t>(g);
-              ro_ng[r] = static_cast<uint32_t>(cnt);
-              ro_slot[r] = static_cast<uint32_t>((n_g0 + g) & smask);
-              g += (cnt > 0) ? cnt : 1;
-            }
-            g = gl;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              int cnt = 0;
-              if (g <= gh) {
-                cnt = 1;
-                if (g + 1 <= gh && (g == 0 ? lf0 : lf1)) {
-                  cnt = 2;
-                  if (g == 0 && gh == 2 && lf1) cnt = 3;
-                }
-                n_rf = r + 1;
-              }
-              rf_g0[r] = static_cast<uint32_t>(g);
-              rf_ng[r] = static_cast<uint32_t>(cnt);
-              rf_slot[r] = static_cast<uint32_t>((n_g0 + g) & smask);
-              rf_acc[r] = (g == 2 || (g == 1 && init1)) ? 0u : 1u;
-              g += (cnt > 0) ? cnt : 1;
-            }
-          }
-          // accumulator addresses / instruction descriptors of the runs in ring 0, of the centre row in ring 1
-          uint32_t od[3], oi[3], fd[3], fi[3];
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            od[r] = d_ring0 + ro_slot[r] * aw0;
-            oi[r] = idesc0 | (((ro_ng[r] * aw0) >> 3) << 17);
-            fd[r] = d_ring0 + rf_slot[r] * aw0;
-            fi[r] = idesc0 | (((rf_ng[r] * aw0) >> 3) << 17);
-          }
-          const uint32_t slot_c = static_cast<uint32_t>((n_g0 + 1) & smask);  // ring slot of the centre row
+          RowRing arB = ar;
+          arB.advance(a.a_slots);
+          RowPlan PA, PB;
+          row_plan(PA, yi, sg, n_base, a.H, smask, sshift, R.aw0, R.d_ring0, R.idesc0);
+          // both barrier polls of the first row (the ring slot it initialises, its A row slot) are issued before the
+          // second row is planned so that their latencies overlap
+          const uint32_t ok_ring = PA.has_init ? mbar_try_wait(&tempty[PA.n_init & smask], PA.init_par) : 1u;
+          const uint32_t ok_a = mbar_try_wait(&afull[ar.idx], ar.phase);
+          if (two) row_plan(PB, yi + 1, sg, n_base, a.H, smask, sshift, R.aw0, R.d_ring0, R.idesc0);
           if (lane == 0) RTL(row_no, 8);
-          if (!ok_ring) row_wait(&tempty[n_init & smask], init_par, a.err, 2);
-          // (row 0 of an image initialises two output rows: the second slot was drained before the first, in order)
-          if (yi == 0 && gl <= 1 && gh == 2) {
-            const int n2 = n_g0 + 2;
+          if (!ok_ring) row_wait(&tempty[PA.n_init & smask], PA.init_par, a.err, 2);
+          // (row 0 of an image initialises two output rows: the second slot was drained after the first, in order)
+          if (PA.init_two) {
+            const int n2 = PA.n_init + 1;
             row_wait(&tempty[n2 & smask], (static_cast<uint32_t>(n2 >> sshift) & 1u) ^ 1u, a.err, 2);
           }
           tc_fence_after();
           if (lane == 0) RTL(row_no, 1);
-          if (!ok_a0) row_wait(&afull[ar.idx], ar.phase, a.err, 2);
+          if (!ok_a) row_wait(&afull[ar.idx], ar.phase, a.err, 2);
           if (lane == 0) RTL(row_no, 2);
           if (elect_one()) {
             RTL(row_no, 9);
-            const uint32_t slot16 = smem_u32(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes) >> 4;
-            int s_begin = 0;
-            {
-              // sub-tiles 0 and 1 from registers, one pass over their taps per run of output rows (one run unless
-              // the ring wraps inside this row's three output rows). Sub-tile 0 is always the first 3x3 term of ring
-              // 0: it carries the initialising MMAs, which cover every output row of this input row.
-              {
-                const uint32_t sub16 = slot16 + (static_cast<uint32_t>(T0.off_kib) << 6);
-                const uint32_t a0 = qa0[0] + sub16, a1 = qa0[1] + sub16, a2 = qa0[2] + sub16;
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-                  if (r < n_rf) umma_bf16_split(fd[r], a0, T0.a_hi, qb0[0] + rf_g0[r] * grp0, T0.b_hi, fi[r], rf_acc[r]);
-                for (int r = 0; r < n_ro; ++r) {  // a runtime loop: the MMA sequences below exist once in the code
-                  const uint32_t d = (r == 0) ? od[0] : ((r == 1) ? od[1] : od[2]);
-                  const uint32_t id = (r == 0) ? oi[0] : ((r == 1) ? oi[1] : oi[2]);
-                  const uint32_t boff = ((r == 0) ? ro_g0[0] : ((r == 1) ? ro_g0[1] : ro_g0[2])) * grp0;
-                  if (T0.nk == 4)
-                    row_issue3<4>(d, id, a0, a1, a2, qb0[0] + boff, qb0[1] + boff, qb0[2] + boff, T0.a_hi, T0.b_hi, 1u);
-                  else if (T0.nk == 2)
-                    row_issue3<2>(d, id, a0, a1, a2, qb0[0] + boff, qb0[1] + boff, qb0[2] + boff, T0.a_hi, T0.b_hi, 1u);
-                  else
-                    row_issue3<1>(d, id, a0, a1, a2, qb0[0] + boff, qb0[1] + boff, qb0[2] + boff, T0.a_hi, T0.b_hi, 1u);
-                }
-                s_begin = 1;
-              }
-              if (fast1) {
-                const uint32_t sub16 = slot16 + (static_cast<uint32_t>(T1.off_kib) << 6);
-                const uint32_t a0 = qa1[0] + sub16, a1 = qa1[1] + sub16, a2 = qa1[2] + sub16;
-                for (int r = 0; r < n_ro; ++r) {
-                  const uint32_t d = (r == 0) ? od[0] : ((r == 1) ? od[1] : od[2]);
-                  const uint32_t id = (r == 0) ? oi[0] : ((r == 1) ? oi[1] : oi[2]);
-                  const uint32_t boff = ((r == 0) ? ro_g0[0] : ((r == 1) ? ro_g0[1] : ro_g0[2])) * grp1;
-                  if (T1.nk == 4)
-                    row_issue3<4>(d, id, a0, a1, a2, qb1[0] + boff, qb1[1] + boff, qb1[2] + boff, T1.a_hi, T1.b_hi, 0u);
-                  else if (T1.nk == 2)
-                    row_issue3<2>(d, id, a0, a1, a2, qb1[0] + boff, qb1[1] + boff, qb1[2] + boff, T1.a_hi, T1.b_hi, 0u);
-                  else
-                    row_issue3<1>(d, id, a0, a1, a2, qb1[0] + boff, qb1[1] + boff, qb1[2] + boff, T1.a_hi, T1.b_hi, 0u);
-                }
-                s_begin = 2;
-              }
-            }
-            for (int s = s_begin; s < a.n_sub; ++s) {
-              const RowSub T = (s == 0) ? T0 : ((s == 1) ? T1 : prog.sub[s]);
-              if (!T.rows3 && !centre) continue;
-              const uint32_t sub16 = slot16 + (static_cast<uint32_t>(T.off_kib) << 6);
-              const uint32_t a_hi = T.a_hi, b_hi = T.b_hi;
-              const int i_end = T.first_mma + T.n_mma;
-              const int nk = T.nk;
-              if (T.rows3) {
-                for (int i = T.first_mma; i < i_end; ++i) {
-                  // one record per horizontal tap: nk MMAs (K = 16 slices) per run
-                  const uint4 q = *reinterpret_cast<const uint4*>(&prog.mma[i]);
-                  const uint32_t a_lo = q.x + sub16, b_lo = q.y + wb;
-                  int k0 = 0;
-                  if (q.w & ROWTAP_RING_FIRST) {
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-                      if (r < n_rf) umma_bf16_split(fd[r], a_lo, a_hi, b_lo + rf_g0[r] * q.z, b_hi, fi[r], rf_acc[r]);
-                    k0 = 1;
-                  }
-                  for (int kk = k0; kk < nk; ++kk) {
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-                      if (r < n_ro)
-                        umma_bf16_split(od[r], a_lo + 2u * kk, a_hi, b_lo + ro_g0[r] * q.z + 2u * kk, b_hi, oi[r], 1u);
-                  }
-                }
-              } else {
-                // 1x1 term: only the centre row; the first K slice of the ring's first tap overwrites
-                const uint32_t dc = (T.ring ? d_ring1 + slot_c * aw1 : d_ring0 + slot_c * aw0);
-                const uint32_t ic = idesc0 | ((static_cast<uint32_t>(T.aw) >> 3) << 17);
-                for (int i = T.first_mma; i < i_end; ++i) {
-                  const uint4 q = *reinterpret_cast<const uint4*>(&prog.mma[i]);
-                  for (int kk = 0; kk < nk; ++kk)
-                    umma_bf16_split(dc, q.x + sub16 + 2u * kk, a_hi, q.y + wb + 2u * kk, b_hi, ic,
-                                    ((q.w & ROWTAP_RING_FIRST) && kk == 0) ? 0u : 1u);
-                }
-              }
-            }
+            row_issue(prog, R, PA, smem_u32(a_base + static_cast<size_t>(ar.idx) * a.a_slot_bytes) >> 4, a.n_sub);
             RTL(row_no, 10);
             // one commit frees the row slot, one (two at the bottom of an image) publishes the completed output rows:
             // the row above this input row, at the bottom of the image also its own
             umma_commit(&aempty[ar.idx]);
+            if (PA.commit_prev) umma_commit(&tfull[PA.slot0]);
+            if (PA.commit_own) umma_commit(&tfull[PA.slot_c]);
             RTL(row_no, 11);
-            if (yi - 1 >= sg.r0) umma_commit(&tfull[slot0]);
-            if (yi == a.H - 1 && sg.r1 == a.H) umma_commit(&tfull[(n_g0 + 1) & smask]);
+            if (two) {
+              // second row: its waits are taken by the issuing lane alone (nobody else touches what they guard)
+              if (PB.has_init) {
+                row_wait(&tempty[PB.n_init & smask], PB.init_par, a.err, 2);
+                tc_fence_after();
+              }
+              row_wait(&afull[arB.idx], arB.phase, a.err, 2);
+              row_issue(prog, R, PB, smem_u32(a_base + static_cast<size_t>(arB.idx) * a.a_slot_bytes) >> 4, a.n_sub);
+              umma_commit(&aempty[arB.idx]);
+              if (PB.commit_prev) umma_commit(&tfull[PB.slot0]);
+              if (PB.commit_own) umma_commit(&tfull[PB.slot_c]);
+            }
           }
           __syncwarp();
           ar.advance(a.a_slots);
+          if (two) ar.advance(a.a_slots);
           if (lane == 0) RTL(row_no, 3);
-          if (lane == 0) RTL(row_no, 12);
         }
         n_base += sg.r1 - sg.r0;
       }

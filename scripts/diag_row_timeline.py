@@ -25,8 +25,8 @@ names = ["start", "ring_ok", "afull0", "issued", "prod", "e_arrive", "e_full", "
 t0 = buf[0]
 print(os.environ.get("DRS_V2_TIMELINE_LAYER"))
 print("row " + " ".join(f"{nm:>8s}" for nm in names))
-for r in range(24):
-    if buf[r * 16] == 0 and r > 0: break
+for r in range(32):
+    if buf[r * 16] == 0 and r > 0: continue   # the issuer stamps every second row (two input rows per iteration)
     print(f"{r:3d} " + " ".join(f"{(buf[r * 16 + s] - t0) if buf[r * 16 + s] else -1:8d}" for s in range(13)))
 nm = C.create_string_buffer(64)
 for i in range(nl):
