@@ -372,8 +372,29 @@ __device__ __forceinline__ void conv_epilogue_std_ct(const EpiArgs& e, uint32_t 
     E.te_pre = e.te + static_cast<size_t>(valid ? __ldg(e.trow + b) : 0) * e.te_stride + e.pre_off +
                (ry * 3 + rx) * e.OC + oc_off;
   }
-  if ((FL & F_ROWSCALE) && valid)
+  if ((FL & F_ROWSCALE) && !(FL & F_GATE) && valid)
     E.rs = __ldg(e.psi + (static_cast<size_t>(b) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1));
+  if (FL & F_GATE) {
+    // Fused attention gate (UNet_model_superres.py:101-106): accumulator columns [0, nvec) hold W_g g + W_x x of this
+    // thread's (gate-resolution) pixel; psi = sigmoid(w_psi . relu(. + b_g + b_x) + b_psi) stays in a register and
+    // scales the four parity groups behind them (same expression, same order as EPI_PSI: both paths agree bitwise).
+    float p = 0.0f;
+    for (int c0 = 0; c0 < e.nvec; c0 += 16) {
+      float v[16];
+      tmem_ld16(taddr + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = c0 + i;
+        p = fmaf(s_par[3][c], fmaxf(fmaf(v[i], 1.0f, s_par[2][c]), 0.0f), p);
+      }
+    }
+    p += __ldg(e.bvec);
+    E.rs = 1.0f / (1.0f + __expf(-p));
+    if (e.psi_out && oc_off == 0 && g_begin == 0 && valid)
+      e.psi_out[(static_cast<size_t>(b) * H + y) * W + x] = E.rs;
+    taddr += static_cast<uint32_t>(e.nvec);  // the groups follow the gate columns
+  }
 
   if (StdEpilogue<FL>::kDual) {
     // two accumulators per chunk: single-buffered (32 registers), which keeps the kernel at two CTAs per SM
@@ -426,12 +447,20 @@ __device__ __forceinline__ void conv_epilogue_std_ct(const EpiArgs& e, uint32_t 
 template <int EPI>
 __device__ __forceinline__ void load_epilogue_params(const EpiArgs& e, int n_sub, int oc_off, float (*s_par)[kMaxN],
                                                      int tid, int nthreads) {
+  const bool gate = (EPI == EPI_STD) && (e.flags & F_GATE);
   for (int c = tid; c < n_sub; c += nthreads) {
     s_par[0][c] = e.scale ? __ldg(e.scale + oc_off + c) : 1.0f;
     s_par[1][c] = e.bias ? __ldg(e.bias + oc_off + c) : 0.0f;
-    if (EPI == EPI_STD) {
+    if (EPI == EPI_STD && !gate) {
       s_par[2][c] = e.scale2 ? __ldg(e.scale2 + oc_off + c) : 1.0f;
       s_par[3][c] = e.bias2 ? __ldg(e.bias2 + oc_off + c) : 0.0f;
+    }
+  }
+  if (gate) {
+    // every split needs the whole gate: bias (b_g + b_x) in scale2, w_psi in wvec, nvec channels
+    for (int c = tid; c < e.nvec; c += nthreads) {
+      s_par[2][c] = __ldg(e.scale2 + c);
+      s_par[3][c] = __ldg(e.wvec + c);
     }
   }
   if (EPI == EPI_PSI) {

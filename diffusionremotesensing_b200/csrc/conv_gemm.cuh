@@ -47,6 +47,8 @@ enum EpiFlags : int {
                      // time vector under zero padding: 9 border classes)
   F_ROWSCALE = 32,   // acc *= psi[b, y/2, x/2] (attention gate commutes with the 1x1 conv)
   F_UPDATE = 64,     // EPI_OUT only: apply the DDPM posterior update in place instead of writing eps
+  F_GATE = 128,      // fused attention gate: the first `nvec` accumulator columns hold W_g g + W_x x; the thread turns
+                     // them into psi = sigmoid(w . relu(. + bias) + b) and uses it as the row scale of the groups
 };
 
 struct EpiArgs {
@@ -67,6 +69,7 @@ struct EpiArgs {
   int te_off;           // offset of this layer's post-add vector inside a row
   int pre_off;          // offset of this layer's 9-class pre-add block inside a row
   const float* psi;     // F_ROWSCALE: [B, H/2, W/2] fp32
+  float* psi_out;       // F_GATE: optional copy of the gate map [B, H, W] fp32 (grid resolution), written by split 0
   const float* wvec;    // EPI_PSI: [N]; EPI_OUT: [nvec, N]
   const float* bvec;    // EPI_PSI: [1]; EPI_OUT: [nvec]
   int nvec;

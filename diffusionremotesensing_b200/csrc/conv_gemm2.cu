@@ -395,6 +395,7 @@ static constexpr int kMaxDynSmem2 = 214 * 1024;
   X(EPI_STD, F_RELU | F_TE | F_DUAL_POST)         \
   X(EPI_STD, F_RELU | F_DUAL_PRE)                 \
   X(EPI_STD, F_ROWSCALE)                          \
+  X(EPI_STD, F_GATE | F_ROWSCALE)                 \
   X(EPI_STD, F_RELU | F_PRE)                      \
   X(EPI_PSI, -1)                                  \
   X(EPI_OUT, -1)

@@ -69,6 +69,9 @@ struct GemmSpec {
   std::string name;
   std::string src_name[2];  // activation tensors read (plan names)
   std::string out_name;     // activation tensor written ("" for EPI_OUT: the caller's eps buffer)
+  std::string psi_name;     // fused gate: fp32 gate map the epilogue also writes (activation taps)
+  double macs_per_px = 0;   // set by builders that do not fill `kblocks` (drs_plan_launch_info)
+  double weight_bytes = 0;
   int epi_kind = EPI_STD;
   int flags = 0;
   int OC = 0;        // channels of the output tensor (EPI_STD) / accumulator width (EPI_PSI, EPI_OUT)
@@ -149,6 +152,7 @@ struct DrsModel {
   long inv_freq = -1, label_emb = -1;
   int n_layers = 0;            // gemms[0 .. n_layers) are the layers, the rest their narrow (32-channel) variants
   std::vector<int> alt;        // alt[i]: index of layer i's narrow variant in gemms, or -1
+  std::vector<int> gate_alt;   // gate_alt[i]: for a psi launch i, index of the fused gate (psi + result) in gemms, or -1
   drs::SmallConv conv0, enc[7], cond_conv;       // enc: blocks.{0,1,2}.conv{1,2}, conv_out
   bool has_cond = false;
 

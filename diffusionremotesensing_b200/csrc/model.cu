@@ -156,6 +156,7 @@ struct Builder {
   // same terms, same epilogue, four (or more) times as many CTAs, each streaming a quarter of the weights. The plan
   // picks the variant per launch (plan.cu); a variant is found through its name.
   std::vector<GemmSpec> narrow;
+  std::vector<GemmSpec> fused_gates;  // "<attention block>.gate": replaces that block's psi + result launches
 
   bool build(GemmSpec& g, const std::vector<ConvTerm>& terms) {
     if (!build_one(g, terms)) return false;
@@ -265,6 +266,147 @@ struct Builder {
     m->kb_all.insert(m->kb_all.end(), g.kblocks.begin(), g.kblocks.end());
     build_v2(g, terms);
     build_row(g, terms);
+    return true;
+  }
+
+  // Fused attention gate (UNet_model_superres.py:101-107) as ONE second-generation program: per tile of 8 x 16 gate-
+  // resolution pixels the K-blocks
+  //     W_g . g            (1x1, source 0)                       -> accumulator columns [0, Ch)
+  //     W_x[py][px] . x    (2x2 stride 2, source 1 seen through its stride-2 view)  -> columns [0, Ch)
+  //     W_r . x[py][px]    (the 1x1 `result` conv on the SAME resident parity plane) -> columns Ch + (2 py + px) n_sub
+  // share the four parity planes of the skip tensor, which the unfused pair of launches reads twice; the epilogue
+  // (F_GATE) turns the first Ch columns into psi and uses it as the row scale of the four parity groups, so the gate
+  // map never travels through memory. Every N split (32 result channels) recomputes the whole gate. Only v2-resident
+  // programs are built (Ch <= 64: decoder stages 1 and 2); the caller keeps the separate launches otherwise.
+  bool build_gate(GemmSpec& g, int Ch, const std::vector<float>& wg, const std::vector<float>& wx,
+                  const std::vector<float>& wr) {
+    GemmSpec::V2& v = g.v2;
+    v.usable = false;
+    // 32-channel blocks: a skip sub-tile (8 x 16 gate pixels x both row parities) is 16 KiB, so six to eight A slots
+    // fit beside the resident weights and the store staging (64-channel blocks would leave two)
+    const int ck = 32;
+    // Only the single-split case (Ch = 32: the full-resolution decoder stage, the most expensive gate) is taken: with
+    // Ch = 64 two splits recompute the gate and reload every A tile, and the pair-of-tiles pipeline runs out of A slots
+    // (measured in-graph at cfg 2: 40 us fused against 34.5 us for the two launches; Ch = 32: 46 against 63).
+    if (Ch != ck) return true;
+    const int pix = ck * 2, nblk = Ch / ck;
+    g.n_sub = 32;
+    g.nsplit = Ch / g.n_sub;
+    g.n_src = 2;
+    g.src_C[0] = g.src_C[1] = Ch;
+    g.src_ck[0] = g.src_ck[1] = ck;
+    g.src_stride2[0] = 0;
+    g.src_stride2[1] = 1;
+    g.nkb = 0;
+    g.kblocks.clear();
+    g.max_a_bytes = kTileM * pix;
+    g.max_b_bytes = Ch * pix;
+    const int n_kb = nblk * (1 + 2 * 2 * 2), n_st = nblk * 3;
+    if (n_kb > kMaxKBlocks || n_st > kMaxSubTiles) return true;
+    const int acc_cols = Ch + 4 * g.n_sub;
+    if (2 * acc_cols > 512) return true;
+    g.tmem_cols = pow2_at_least(acc_cols, 32);
+    v.halo_w[0] = kTile2W; v.halo_h[0] = kTile2H; v.npy[0] = 1;
+    v.halo_w[1] = kTile2W; v.halo_h[1] = kTile2H; v.npy[1] = 2;
+    v.a_slot_bytes = (pix * kTile2W * 2 * kTile2H + 1023) & ~1023;
+    const size_t tile_g = (static_cast<size_t>(Ch) * pix + 1023) & ~static_cast<size_t>(1023);
+    const size_t tile_r = (static_cast<size_t>(g.n_sub) * pix + 1023) & ~static_cast<size_t>(1023);
+    const size_t w_image = nblk * tile_g + static_cast<size_t>(nblk) * 4 * (tile_g + tile_r);
+    if (w_image + 2 * static_cast<size_t>(v.a_slot_bytes) > 200 * 1024) return true;  // resident programs only
+    v.resident = true;
+    v.b_unit = 1;
+    v.b_stage_bytes = static_cast<int>(tile_g);
+    v.w_split_bytes = static_cast<uint32_t>(w_image);
+    while (m->wblob.size() % 1024) m->wblob.push_back(0);
+    v.w_split_off = static_cast<uint32_t>(m->wblob.size());
+    m->wblob.resize(m->wblob.size() + w_image * g.nsplit);
+    Conv2Prog& P = v.prog;
+    memset(&P, 0, sizeof(P));
+    const uint32_t mask = static_cast<uint32_t>(pix / 16 - 1);
+    auto pack = [&](uint8_t* tile, int rows, auto weight_of) {
+      for (int r = 0; r < rows; ++r)
+        for (int k = 0; k < ck; ++k) {
+          uint32_t o = static_cast<uint32_t>(r * pix + k * 2);
+          o ^= ((o >> 7) & mask) << 4;
+          const uint16_t h = f32_to_bf16(weight_of(r, k));
+          memcpy(tile + o, &h, 2);
+        }
+    };
+    for (int s = 0; s < g.nsplit; ++s) {
+      uint8_t* image = m->wblob.data() + v.w_split_off + static_cast<size_t>(s) * w_image;
+      size_t off = 0;
+      int kb = 0, st = 0;
+      bool col_seen[5] = {false, false, false, false, false};  // gate columns, four parity groups
+      auto emit = [&](int a_off, uint32_t sbo_bytes, int n, int col, int seen_idx, bool first, bool last, size_t tile_bytes) {
+        if (s == 0) {
+          KB3& K = P.kb[kb];
+          K.a_lo = static_cast<uint32_t>(a_off / 16) | 0x10000u;
+          K.a_hi = umma_desc_hi(pix, sbo_bytes);
+          K.b_lo = static_cast<uint32_t>(off / 16) | 0x10000u;
+          K.b_hi = umma_desc_hi(pix, 8 * pix);
+          K.idesc = umma_idesc_host(kTileM, n);
+          K.col = static_cast<uint16_t>(col);
+          K.nk = static_cast<uint8_t>(ck / 16);
+          K.flags = static_cast<uint8_t>((col_seen[seen_idx] ? 0 : KB2_INIT) | (first ? KB2_FIRST : 0) | (last ? KB2_LAST : 0));
+          K.b_off = static_cast<uint32_t>(off);
+          K.b_bytes = static_cast<uint32_t>(n * pix);
+        }
+        col_seen[seen_idx] = true;
+        off += tile_bytes;
+        ++kb;
+      };
+      // source 0: the gating signal, one K-block per channel block
+      for (int c0 = 0; c0 < Ch; c0 += ck) {
+        if (s == 0) {
+          SubTile& T = P.st[st];
+          T.c = c0; T.dx0 = 0; T.dy0 = 0; T.src = 0;
+          T.bytes = static_cast<uint32_t>(pix * kTile2W * kTile2H);
+        }
+        ++st;
+        pack(image + off, Ch, [&](int r, int k) { return wg[static_cast<size_t>(r) * Ch + c0 + k]; });
+        emit(0, static_cast<uint32_t>(kTile2W * pix), Ch, 0, 0, true, true, tile_g);
+      }
+      // source 1: the skip tensor through its stride-2 view; sub-tile = (column parity, channel block), both row
+      // parities inside; per row parity one gate K-block and one result K-block on the same A rows
+      for (int px = 0; px < 2; ++px) {
+        for (int c0 = 0; c0 < Ch; c0 += ck) {
+          if (s == 0) {
+            SubTile& T = P.st[st];
+            T.c = px * Ch + c0; T.dx0 = 0; T.dy0 = 0; T.src = 1;
+            T.bytes = static_cast<uint32_t>(pix * kTile2W * 2 * kTile2H);
+          }
+          ++st;
+          for (int py = 0; py < 2; ++py) {
+            const int a_off = kTile2W * py * pix;
+            const uint32_t sbo = static_cast<uint32_t>(kTile2W * 2 * pix);
+            pack(image + off, Ch, [&](int r, int k) {
+              return wx[((static_cast<size_t>(r) * Ch + c0 + k) * 2 + py) * 2 + px];
+            });
+            emit(a_off, sbo, Ch, 0, 0, py == 0, false, tile_g);
+            pack(image + off, g.n_sub, [&](int r, int k) {
+              return wr[static_cast<size_t>(s * g.n_sub + r) * Ch + c0 + k];
+            });
+            const int grp = (py << 1) | px;
+            emit(a_off, sbo, g.n_sub, Ch + grp * g.n_sub, 1 + grp, false, py == 1, tile_r);
+          }
+        }
+      }
+      if (s == 0) {
+        v.nkb = kb;
+        v.n_sub_tiles = st;
+      }
+    }
+    for (int i = 0; i < v.nkb; ++i) {
+      if (!(P.kb[i].flags & KB2_FIRST)) continue;
+      int cnt = 1;
+      while (!(P.kb[i + cnt - 1].flags & KB2_LAST)) ++cnt;
+      P.kb[i].b_bytes |= static_cast<uint32_t>(cnt) << 24;
+    }
+    v.acc_cols = acc_cols;
+    v.usable = true;
+    // algorithmic work per gate-resolution pixel (drs_plan_launch_info): gate 5 Ch^2 MACs, result 4 Ch^2
+    g.macs_per_px = 9.0 * Ch * Ch;
+    g.weight_bytes = static_cast<double>(w_image) * g.nsplit;
     return true;
   }
 
@@ -680,6 +822,15 @@ static void append_narrow(DrsModel* m, Builder& B) {
     m->gemms.push_back(std::move(n));
   }
   B.narrow.clear();
+  // fused gates: linked from their psi launch
+  m->gate_alt.assign(m->gemms.size(), -1);
+  for (GemmSpec& f : B.fused_gates) {
+    const std::string psi_name = f.name.substr(0, f.name.size() - 4) + "psi";
+    for (int i = 0; i < m->n_layers; ++i)
+      if (m->gemms[i].name == psi_name) m->gate_alt[i] = static_cast<int>(m->gemms.size());
+    m->gemms.push_back(std::move(f));
+  }
+  B.fused_gates.clear();
 }
 
 static bool build_model(DrsModel* m) {
@@ -852,6 +1003,29 @@ static bool build_model(DrsModel* m) {
       if (!B.build(g, {term(0, Ch, CONV_1x1, {wref(w, Ch, Ch)})})) return false;
       g.n_src = 1;
       m->gemms.push_back(std::move(g));
+      // fused form of the two launches above (taken by the plan where its program is resident and the grid holds a
+      // tile): parameters = result's folded BatchNorm (per output channel) + the whole gate (bias sum, w_psi, b_psi)
+      GemmSpec f;
+      f.name = ab + ".gate";
+      f.src_name[0] = "g" + si;
+      f.src_name[1] = skip;
+      f.out_name = "att" + si;
+      f.psi_name = "psi" + si;
+      f.OC = Ch;
+      f.n_groups = 4;
+      f.oscale = 2;
+      f.flags = F_GATE | F_ROWSCALE;
+      f.scale = m->gemms.back().scale;
+      f.bias = m->gemms.back().bias;
+      const GemmSpec& psi_spec = m->gemms[m->gemms.size() - 2];
+      f.scale2 = psi_spec.bias;   // b_g + b_x
+      f.wvec = psi_spec.wvec;
+      f.bvec = psi_spec.bvec;
+      f.nvec = Ch;
+      const auto* wg2 = B.get(ab + ".w_g.0.weight", static_cast<size_t>(Ch) * Ch);
+      const auto* wx2 = B.get(ab + ".w_x.0.weight", static_cast<size_t>(Ch) * Ch * 4);
+      if (!wg2 || !wx2 || !B.build_gate(f, Ch, *wg2, *wx2, *w)) return false;
+      if (f.v2.usable) B.fused_gates.push_back(std::move(f));
     }
     // UpConvBlock conv: relu(bn(conv3x3(x + relu(time_mlp(t)))))   (:197-205)
     const std::string ub = "ups." + si;

@@ -137,6 +137,7 @@ static int bind_launch(DrsPlan* p, int spec_idx, const void* src0, const void* s
     stages = std::min({budget / a.stage_bytes, 8, g.nkb});
     if (stages >= 3 || stages >= g.nkb || ctas == 1) break;
   }
+  if (g.kblocks.empty()) stages = 1;  // second-generation-only program (fused gate): no first-generation pipeline
   if (stages < 1) {
     set_error("%s: stage of %d bytes does not fit shared memory", g.name.c_str(), a.stage_bytes);
     return DRS_E_INVALID;
@@ -165,6 +166,7 @@ static int bind_launch(DrsPlan* p, int spec_idx, const void* src0, const void* s
   e.wvec = m->f(g.wvec);
   e.bvec = m->f(g.bvec);
   e.nvec = g.nvec;
+  e.psi_out = nullptr;
   return DRS_OK;
 }
 
@@ -589,6 +591,7 @@ int plan_create(DrsModel* m, int nb, int nx, int ncond, int S, int mag, DrsPlan*
   // launch list
   uint8_t* ws = p->workspace.as<uint8_t>();
   const size_t n_layers = m->n_layers > 0 ? static_cast<size_t>(m->n_layers) : m->gemms.size();
+  bool skip_next_result = false;
   for (size_t li = 0; li < n_layers; ++li) {
     // Small grids: when the wide form of a launch would occupy less than half of the SMs, its narrow variant (32 output
     // channels per CTA) spreads the K loop and the weight streaming over four or more times as many CTAs.
@@ -602,6 +605,25 @@ int plan_create(DrsModel* m, int nb, int nx, int ncond, int S, int mag, DrsPlan*
       const long ctas_wide = ((tiles + 1) / 2) * w.nsplit;
       if (li < m->alt.size() && m->alt[li] >= 0 && gh >= kTile2H && gw >= kTile2W && ctas_wide < narrow_below)
         gi = static_cast<size_t>(m->alt[li]);
+    }
+    // Attention gate: the fused program (psi + result in one launch, conv_gemm2 only) replaces the pair when the
+    // model built one for this block, the grid holds an 8 x 16 tile and neither DRS_NO_GATE_FUSION nor the generic
+    // epilogue is requested; the result launch that follows is then skipped.
+    {
+      static const bool no_fuse = getenv("DRS_NO_GATE_FUSION") || getenv("DRS_V2_GENERIC_EPILOGUE") ||
+                                  getenv("DRS_DISABLE_V2");
+      if (skip_next_result) {
+        skip_next_result = false;
+        continue;
+      }
+      if (!no_fuse && li < m->gate_alt.size() && m->gate_alt[li] >= 0) {
+        const GemmSpec& f = m->gemms[m->gate_alt[li]];
+        const ActTensor& gs = p->acts.at(f.src_name[0]);
+        if (gs.H >= kTile2H && gs.W >= kTile2W) {
+          gi = static_cast<size_t>(m->gate_alt[li]);
+          skip_next_result = true;
+        }
+      }
     }
     const GemmSpec& g = m->gemms[gi];
     const ActTensor& s0 = p->acts.at(g.src_name[0]);
@@ -635,8 +657,14 @@ int plan_create(DrsModel* m, int nb, int nx, int ncond, int S, int mag, DrsPlan*
     }
     Launch L;
     DRS_TRY(bind_launch(p.get(), static_cast<int>(gi), src[0], src[1], gridW, gridH, sH, sW, outp, OH, OW, &L));
-    if (g.flags & F_ROWSCALE) L.args.epi.psi = reinterpret_cast<const float*>(ws + p->acts.at(g.src_name[1]).offset);
+    if ((g.flags & F_ROWSCALE) && !(g.flags & F_GATE))
+      L.args.epi.psi = reinterpret_cast<const float*>(ws + p->acts.at(g.src_name[1]).offset);
+    if (g.flags & F_GATE) L.args.epi.psi_out = reinterpret_cast<float*>(ws + p->acts.at(g.psi_name).offset);
     DRS_TRY(bind_launch_v2(p.get(), src[0], src[1], gridW, gridH, sH, sW, &L));
+    if ((g.flags & F_GATE) && !L.use_v2) {
+      set_error("%s: the fused gate program could not be bound", g.name.c_str());
+      return DRS_E_INVALID;
+    }
     DRS_TRY(bind_launch_cg2(p.get(), &L));
     if (!(g.flags & F_ROWSCALE)) DRS_TRY(bind_launch_row(p.get(), src[0], src[1], gridW, gridH, sH, sW, &L));
     p->launches.push_back(L);
@@ -1164,6 +1192,10 @@ int launch_info(const DrsPlan* p, int i, char* name, int name_cap, double* flops
     macs += static_cast<double>(kb.n) * kb.ck;
     wbytes += kb.b_bytes;
   }
+  if (g.kblocks.empty()) {
+    macs = g.macs_per_px;
+    wbytes = g.weight_bytes;
+  }
   if (name) snprintf(name, name_cap, "%s", g.name.c_str());
   if (flops) {
     *flops = 2.0 * grid_px * macs;
@@ -1176,7 +1208,7 @@ int launch_info(const DrsPlan* p, int i, char* name, int name_cap, double* flops
       const ActTensor& t = p->acts.at(g.src_name[s]);
       b += static_cast<double>(p->nb) * t.H * t.W * t.C * 2;
     }
-    if (g.flags & F_ROWSCALE) b += grid_px;  // psi map, fp32 at quarter resolution
+    if ((g.flags & F_ROWSCALE) && !(g.flags & F_GATE)) b += grid_px;  // psi map, fp32 at quarter resolution
     if (g.epi_kind == EPI_OUT)
       b += grid_px * g.nvec * 4;
     else if (g.epi_kind == EPI_PSI)

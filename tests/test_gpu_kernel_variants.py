@@ -8,6 +8,7 @@ path (tests/test_gpu_conv_layers.py):
   * DRS_V2_NO_SOLO=1        transposed convolutions drained by one epilogue group per tile
   * DRS_DISABLE_V2=1        first-generation kernel for every layer
   * DRS_NO_NARROW=1         no 32-channel launch variants on small grids (the default test sizes otherwise use them)
+  * DRS_NO_GATE_FUSION=1    attention gate as two launches (psi map through memory) instead of the fused program
   * DRS_ROW=force / DRS_ROW=0  row-streaming kernel (conv_row.cu) on every layer it can express whatever the grid
                             size / on none (the second-generation kernel for everything)
 """
@@ -69,3 +70,9 @@ def test_parity_without_row_kernel(cuda_device):
                                      "tests/test_gpu_baseline_configs.py::test_cfg2_batch16_trajectory_vs_oracle"])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "row kernel" not in r.stderr and "row kernel" not in r.stdout
+
+
+def test_unet_parity_without_gate_fusion(cuda_device):
+    r = run_child({"DRS_NO_GATE_FUSION": "1"}, ["tests/test_gpu_unet.py",
+                                                "tests/test_gpu_full_size.py::test_full_resolution_eps_matches_oracle"])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
