@@ -43,17 +43,25 @@ def partition_blocks(n_items: int, world_size: int) -> List[Tuple[int, int]]:
     return out
 
 
+GATHER_CHUNK_BYTES = 64 << 20
+
+
 def gather_blocks(local: torch.Tensor, counts: Sequence[int], dst: int = 0, group=None) -> Optional[torch.Tensor]:
     """Gathers per-rank blocks [counts[r], ...] to rank `dst` in rank order (the one collective of the path).
-    Point-to-point: every rank sends its block once, `dst` receives each block straight into its slice of the result
-    (no padding to the largest block, no staging copies); empty blocks are skipped on both sides."""
+    Point-to-point: every rank sends its block, `dst` receives it straight into its slice of the result (no padding
+    to the largest block, no staging copies); empty blocks are skipped on both sides. Blocks travel in pieces of at
+    most 64 MB (whole items): the first NCCL transfer of a several-hundred-MB buffer was measured at ~3 GB/s on two
+    GPUs (115 ms for 378 MB) against 260-420 GB/s for 94 MB messages."""
     import torch.distributed as dist
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
     local = local.contiguous()
+    item_bytes = max(1, local[0].numel() * local.element_size()) if local.shape[0] else 1
+    per_chunk = max(1, GATHER_CHUNK_BYTES // item_bytes)
+    peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
     if rank != dst:
-        if counts[rank] > 0:
-            dist.send(local, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+        for i in range(0, counts[rank], per_chunk):
+            dist.send(local[i:min(i + per_chunk, counts[rank])], dst=peer(dst), group=group)
         return None
     out = torch.empty((sum(counts),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     offs = [0]
@@ -62,10 +70,10 @@ def gather_blocks(local: torch.Tensor, counts: Sequence[int], dst: int = 0, grou
     out[offs[dst]:offs[dst + 1]] = local
     reqs = []
     for r in range(world):
-        if r == dst or counts[r] == 0:
+        if r == dst:
             continue
-        src = dist.get_global_rank(group, r) if group is not None else r
-        reqs.append(dist.irecv(out[offs[r]:offs[r + 1]], src=src, group=group))
+        for i in range(0, counts[r], per_chunk):
+            reqs.append(dist.irecv(out[offs[r] + i:offs[r] + min(i + per_chunk, counts[r])], src=peer(r), group=group))
     for q in reqs:
         q.wait()
     return out
