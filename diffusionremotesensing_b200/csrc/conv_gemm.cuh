@@ -47,6 +47,8 @@ enum EpiFlags : int {
                      // time vector under zero padding: 9 border classes)
   F_ROWSCALE = 32,   // acc *= psi[b, y/2, x/2] (attention gate commutes with the 1x1 conv)
   F_UPDATE = 64,     // EPI_OUT only: apply the DDPM posterior update in place instead of writing eps
+  F_NOSCALE = 256,   // no per-channel scale (plain conv bias, no BatchNorm): the epilogue adds the bias and skips the
+                     // scale vector's shared-memory reads (set by the plan, compile-time epilogues only)
   F_GATE = 128,      // fused attention gate: the first `nvec` accumulator columns hold W_g g + W_x x; the thread turns
                      // them into psi = sigmoid(w . relu(. + bias) + b) and uses it as the row scale of the groups
 };

@@ -390,6 +390,7 @@ static constexpr int kMaxDynSmem2 = 214 * 1024;
 #define DRS_GEMM2_VARIANTS(X)                     \
   X(EPI_STD, -1)                                  \
   X(EPI_STD, 0)                                   \
+  X(EPI_STD, F_NOSCALE)                           \
   X(EPI_STD, F_RELU)                              \
   X(EPI_STD, F_RELU | F_TE)                       \
   X(EPI_STD, F_RELU | F_TE | F_DUAL_POST)         \

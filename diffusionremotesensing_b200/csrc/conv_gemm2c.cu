@@ -381,6 +381,7 @@ conv_gemm2c_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
 
 #define DRS_GEMM2C_VARIANTS(X) \
   X(0)                         \
+  X(F_NOSCALE)                 \
   X(F_RELU)                    \
   X(F_RELU | F_TE)             \
   X(F_RELU | F_DUAL_PRE)       \

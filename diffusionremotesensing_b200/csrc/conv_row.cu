@@ -552,6 +552,7 @@ static constexpr int kMaxDynSmemRow = 214 * 1024;
 // every instantiation: (EPI, FL) -- the flag words of the layers this kernel serves
 #define DRS_ROW_VARIANTS(X)                       \
   X(EPI_STD, 0)                                   \
+  X(EPI_STD, F_NOSCALE)                           \
   X(EPI_STD, F_RELU)                              \
   X(EPI_STD, F_RELU | F_TE)                       \
   X(EPI_STD, F_RELU | F_TE | F_DUAL_POST)         \

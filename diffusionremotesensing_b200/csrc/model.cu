@@ -176,6 +176,8 @@ struct Builder {
 
   // Appends the K-blocks of `terms` for every N-split and packs the weight tiles.
   bool build_one(GemmSpec& g, const std::vector<ConvTerm>& terms) {
+    // plain conv bias without BatchNorm (downs, transposed convs, up_convs): the epilogue skips the scale vector
+    if (g.epi_kind == EPI_STD && g.scale < 0 && g.flags == 0) g.flags = F_NOSCALE;
     g.nsplit = g.OC / g.n_sub;
     if (g.nsplit * g.n_sub != g.OC || g.n_sub % 16) {
       set_error("%s: bad split OC=%d n_sub=%d", g.name.c_str(), g.OC, g.n_sub);
