@@ -284,6 +284,7 @@ struct StdEpilogue {
   float rs;
   bool valid;
   int oc_off;
+  int tl_slot = 0;  // DRS_EPI_TRACE: first trace slot of the chunk being processed
 
   // scale / pack / store one chunk of 16 channels starting at channel c0 of column group g
   __device__ __forceinline__ void chunk(const uint32_t (&rv)[16], const uint32_t (&rw)[16], int g, int c0) {
@@ -323,6 +324,7 @@ struct StdEpilogue {
       pk[2 * q] = pack_bf16(x0, x1);
       pk[2 * q + 1] = pack_bf16(x2, x3);
     }
+    EPI_TL(tl_slot + 2);
     if (ts) {
       const int cs = c0 & (ts->sbc - 1);  // first channel of this chunk inside its sub-box
       if (cs == 0) {
@@ -430,6 +432,7 @@ __device__ __forceinline__ void conv_epilogue_std_ct(const EpiArgs& e, uint32_t 
         tmem_ld16_raw(colbase + c0 + 16, vb);
         if (StdEpilogue<FL>::kDual) tmem_ld16_raw(taddr + e.col2 + c0 + 16, wb);
       }
+      E.tl_slot = ((g - g_begin) * (N >> 4) + (c0 >> 4)) * 4;
       E.chunk(va, wa, g, c0);
       EPI_TL(((g - g_begin) * (N >> 4) + (c0 >> 4)) * 4 + 3);
       if (has_b) {
@@ -443,12 +446,91 @@ __device__ __forceinline__ void conv_epilogue_std_ct(const EpiArgs& e, uint32_t 
           tmem_ld16_raw(colbase + N, va);
           if (StdEpilogue<FL>::kDual) tmem_ld16_raw(taddr + e.col2, wa);
         }
+        E.tl_slot = ((g - g_begin) * (N >> 4) + (c0 >> 4) + 1) * 4;
         E.chunk(vb, wb, g, c0 + 16);
         EPI_TL(((g - g_begin) * (N >> 4) + (c0 >> 4) + 1) * 4 + 3);
       } else if (more_groups) {
         tmem_ld16_raw(colbase + N, va);  // N == 16: no overlap (does not occur in the three UNets)
         if (StdEpilogue<FL>::kDual) tmem_ld16_raw(taddr + e.col2, wa);
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Transposed convolution, 64 output channels per CTA, bias only (F_NOSCALE | F_TR64), TMA stores. The chunked
+// epilogue above spends ~700 cycles per 16 channels on these layers (4 x 64 columns per tile and nothing to hide
+// them behind: profiles/epilogue_trace_r2.txt): two rounds of parameter reads behind the shared-memory traffic of the
+// MMAs, runtime sub-box bookkeeping on the uniform datapath and a branch every few instructions. Here the 64 biases
+// live in registers for the whole kernel (they are the same for the four phases), a phase group is two 32-column
+// TMEM loads (the second in flight under the math of the first), and the loop body is straight-line code: add, pack,
+// eight 16-byte staging stores, one TMA store of the warp's 32 pixels x 64 channels. Same arithmetic (fp32 add,
+// round-to-nearest-even pack), so the results are bit-identical to the chunked path.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_x32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                 "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                 "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// half: 0 / 1 = channels [0, 32) / [32, 64) of the group; `row` = this lane's 128-byte staging row, `sw` its swizzle
+__device__ __forceinline__ void tr64_half(const uint32_t (&v)[32], const float (&bias)[64], int half, uint32_t row,
+                                          uint32_t sw) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = 8 * j + 2 * i;
+      pk[i] = pack_bf16(__uint_as_float(v[c]) + bias[32 * half + c], __uint_as_float(v[c + 1]) + bias[32 * half + c + 1]);
+    }
+    st_shared_v4(row + ((static_cast<uint32_t>(half * 4 + j) << 4) ^ sw), pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// Staged stores only: per-thread 32-byte global stores of the phase scatter were measured slower than the chunked
+// path (ups.1.transform 43.4 against 41.9 us), so launches without a staging area keep the chunked epilogue.
+__device__ __forceinline__ void conv_epilogue_tr64(const EpiArgs& e, uint32_t taddr, int oc_off, const float (&bias)[64],
+                                                   TmaStoreCtx* ts, int g_begin, int g_end) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t row = smem_u32(ts->stage) + lane * 128u;
+  const uint32_t sw = (lane & 7u) << 4;
+  uint32_t va[32], vb[32];
+  tmem_ld32_raw(taddr + static_cast<uint32_t>(g_begin * 64), va);
+  for (int g = g_begin; g < g_end; ++g) {
+    const uint32_t col = taddr + static_cast<uint32_t>(g * 64);
+    tmem_ld_wait_x32(va);
+    tmem_ld32_raw(col + 32u, vb);
+    // the staging rows are reused by every group: the TMA unit must have read the previous one
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+    tr64_half(va, bias, 0, row, sw);
+    tmem_ld_wait_x32(vb);
+    if (g + 1 < g_end) tmem_ld32_raw(col + 64u, va);
+    tr64_half(vb, bias, 1, row, sw);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_5d(ts->map, reinterpret_cast<const void*>(ts->stage), (g & 1) * e.OC + oc_off, ts->x0, g >> 1, ts->y0,
+                   ts->b);
+      bulk_commit();
     }
   }
 }

@@ -49,6 +49,8 @@ enum EpiFlags : int {
   F_UPDATE = 64,     // EPI_OUT only: apply the DDPM posterior update in place instead of writing eps
   F_NOSCALE = 256,   // no per-channel scale (plain conv bias, no BatchNorm): the epilogue adds the bias and skips the
                      // scale vector's shared-memory reads (set by the plan, compile-time epilogues only)
+  F_TR64 = 512,      // with F_NOSCALE: transposed convolution (four phase groups), 64 channels per CTA, bias only ->
+                     // the register-resident epilogue conv_epilogue_tr64 (set by the model builder)
   F_GATE = 128,      // fused attention gate: the first `nvec` accumulator columns hold W_g g + W_x x; the thread turns
                      // them into psi = sigmoid(w . relu(. + bias) + b) and uses it as the row scale of the groups
 };

@@ -318,6 +318,14 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     // pipeline.
     const int n_jobs = a.solo ? 2 : 1;
     const int g_half = e.n_groups >> 1;
+    // F_TR64: the CTA's 64 biases stay in registers (conv_epilogue_tr64); any other geometry takes the chunked path
+    constexpr bool kTr64 = (EPI == EPI_STD && FL >= 0 && (FL & F_TR64) != 0);
+    const bool tr64 = kTr64 && a.store_sbc == 64 && a.n_sub == 64 && e.oscale == 2;
+    float tr_bias[kTr64 ? 64 : 1];
+    if constexpr (kTr64) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) tr_bias[i] = s_par[1][i];
+    }
     for (int tile0 = first_tile; tile0 < a.n_tiles; tile0 += 2 * tile_step, ++pno) {
       for (int job = 0; job < n_jobs; ++job) {
         const int pp = a.solo ? job : p;  // pipeline whose tile is drained
@@ -354,7 +362,13 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
         if (threadIdx.x == 0 && blockIdx.x == 0) g_epi_trace_on = ((a.timeline & 1) && pno == 3) ? 1 : 0;
 #endif
         if (!(a.timeline & 2)) {
-          if constexpr (EPI == EPI_STD && FL >= 0)
+          if constexpr (EPI == EPI_STD && FL >= 0 && (FL & F_TR64) != 0) {
+            if (tr64)
+              conv_epilogue_tr64(e, taddr, oc_off, tr_bias, &ts, g_begin, g_end);
+            else
+              conv_epilogue_std_ct<(FL & ~F_TR64)>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par,
+                                                  s_te[kStageTe ? warp : 0], a.store_sbc ? &ts : nullptr, g_begin, g_end);
+          } else if constexpr (EPI == EPI_STD && FL >= 0)
             conv_epilogue_std_ct<FL>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par,
                                      s_te[kStageTe ? warp : 0], a.store_sbc ? &ts : nullptr, g_begin, g_end);
           else
@@ -385,12 +399,15 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
 }
 
 static constexpr int kMaxDynSmem2 = 214 * 1024;
+// the transposed-convolution variant (4.6 KiB static) may take what is left of the 227 KiB of a CTA
+static constexpr int kMaxDynSmem2Tr = 222 * 1024;
 
 // every instantiation: (EPI, FL)
 #define DRS_GEMM2_VARIANTS(X)                     \
   X(EPI_STD, -1)                                  \
   X(EPI_STD, 0)                                   \
   X(EPI_STD, F_NOSCALE)                           \
+  X(EPI_STD, F_NOSCALE | F_TR64)                  \
   X(EPI_STD, F_RELU)                              \
   X(EPI_STD, F_RELU | F_TE)                       \
   X(EPI_STD, F_RELU | F_TE | F_DUAL_POST)         \
@@ -405,7 +422,8 @@ int conv_gemm2_set_smem_limits() {
   cudaError_t e = cudaSuccess;
 #define X(EPI, FL)                                                                                              \
   if (e == cudaSuccess)                                                                                         \
-    e = cudaFuncSetAttribute(conv_gemm2_kernel<EPI, (FL)>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem2);
+    e = cudaFuncSetAttribute(conv_gemm2_kernel<EPI, (FL)>, cudaFuncAttributeMaxDynamicSharedMemorySize,                   \
+                             ((FL) >= 0 && ((FL) & F_TR64)) ? kMaxDynSmem2Tr : kMaxDynSmem2);
   DRS_GEMM2_VARIANTS(X)
 #undef X
   return static_cast<int>(e);

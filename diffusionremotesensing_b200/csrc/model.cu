@@ -177,7 +177,11 @@ struct Builder {
   // Appends the K-blocks of `terms` for every N-split and packs the weight tiles.
   bool build_one(GemmSpec& g, const std::vector<ConvTerm>& terms) {
     // plain conv bias without BatchNorm (downs, transposed convs, up_convs): the epilogue skips the scale vector
-    if (g.epi_kind == EPI_STD && g.scale < 0 && g.flags == 0) g.flags = F_NOSCALE;
+    if (g.epi_kind == EPI_STD && g.scale < 0 && (g.flags & ~(F_NOSCALE | F_TR64)) == 0) {
+      g.flags = F_NOSCALE;
+      // transposed convolution with 64 channels per CTA: biases in registers (conv_epilogue_tr64, conv_gemm2 only)
+      if (g.oscale == 2 && g.n_groups == 4 && g.n_sub == 64) g.flags |= F_TR64;
+    }
     g.nsplit = g.OC / g.n_sub;
     if (g.nsplit * g.n_sub != g.OC || g.n_sub % 16) {
       set_error("%s: bad split OC=%d n_sub=%d", g.name.c_str(), g.OC, g.n_sub);

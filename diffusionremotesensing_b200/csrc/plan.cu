@@ -256,12 +256,15 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   int ctas = std::min(512 / alloc, 2);
   int slots = 0;
   for (; ctas >= 1; --ctas) {
-    const int budget = (227 * 1024) / ctas - 14 * 1024 - b_bytes;
+    // (the register-resident transposed epilogue is worth its staging area even with two A slots: 6 KiB cover the
+    // static shared memory, the alignment slack and the per-CTA system reserve when the CTA has the SM to itself)
+    const bool tr64 = (g.flags & F_TR64) != 0 && ctas == 1;
+    const int budget = (227 * 1024) / ctas - (tr64 ? 6 : 14) * 1024 - b_bytes;
     // An even ring gives every slot to exactly one of the two issuers: a consumer that shared a slot with the
     // other issuer would skip every second phase of its full barrier, and a parity wait cannot tell phase k from
     // phase k + 2.
     stage_bytes = 0;
-    if (can_stage && (((budget - kStageBytes) / v.a_slot_bytes) & ~1) >= 4) stage_bytes = kStageBytes;
+    if (can_stage && (((budget - kStageBytes) / v.a_slot_bytes) & ~1) >= (tr64 ? 2 : 4)) stage_bytes = kStageBytes;
     slots = std::min(want_slots, (budget - stage_bytes) / v.a_slot_bytes) & ~1;
     if (slots >= 4 || ctas == 1) break;
   }
@@ -286,6 +289,11 @@ static int bind_launch_v2(DrsPlan* p, const void* src0, const void* src1, int gr
   if (grid < g.nsplit) grid = g.nsplit;
   L->grid2 = grid;
   L->use_v2 = true;
+  static const bool verbose = (getenv("DRS_V2_VERBOSE") != nullptr);
+  if (verbose)
+    fprintf(stderr, "[drs] %s: conv_gemm2, grid %d (%d per SM), %s weights (%d KiB), %d A slots of %d B, staging %d B, "
+            "TMEM %d columns, flags %d\n", g.name.c_str(), grid, ctas, a.resident ? "resident" : "streamed",
+            b_bytes / 1024, slots, v.a_slot_bytes, stage_bytes, alloc, g.flags);
   return DRS_OK;
 }
 
