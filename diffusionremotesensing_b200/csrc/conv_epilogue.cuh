@@ -293,7 +293,7 @@ struct StdEpilogue {
     for (int q = 0; q < 4; ++q) {
       const int c = c0 + 4 * q;
       // Parameter reads go through the shared-memory pipe the MMAs saturate: with none at all the step is 3 % faster
-      // (timing experiment, profiles/epilogue_param_reads_r2.txt), so the scale vector is skipped where it is 1.
+      // (timing experiment, profiles/epilogue_trace_r2.txt), so the scale vector is skipped where it is 1.
       const float4 sc = (FL & F_NOSCALE) ? make_float4(1.f, 1.f, 1.f, 1.f)
                                          : *reinterpret_cast<const float4*>(&s_par[0][c]);
       const float4 bi = *reinterpret_cast<const float4*>(&s_par[1][c]);
@@ -532,6 +532,72 @@ __device__ __forceinline__ void conv_epilogue_tr64(const EpiArgs& e, uint32_t ta
                    ts->b);
       bulk_commit();
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused attention gate with 32 channels (F_GATE | F_ROWSCALE, the full-resolution gate of the UNets), TMA stores:
+// the same idea as conv_epilogue_tr64. The folded BatchNorm of the result conv (32 scales, 32 biases - the same for
+// the four parity groups) stays in registers for the whole kernel, psi comes from one 32-column TMEM load, every
+// parity group is one 32-column load (the next in flight under the math), four 16-byte staging stores and one TMA
+// store of 32 pixels x 32 channels into one of the warp's two 2 KiB buffers. Expressions and their order are those
+// of conv_epilogue_std_ct<F_GATE | F_ROWSCALE>, so both paths agree bitwise.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gate32_group(const uint32_t (&v)[32], float rs, const float (&sc)[32],
+                                             const float (&bi)[32], const EpiArgs& e, TmaStoreCtx* ts, uint32_t row,
+                                             uint32_t sw, int g, uint32_t lane) {
+  // the buffer about to be overwritten must have been read by the store issued two groups ago
+  if (lane == 0) bulk_wait_read<1>();
+  __syncwarp();
+  const uint32_t buf = row + static_cast<uint32_t>(ts->buf) * 2048u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = 8 * j + 2 * i;
+      const float x0 = fmaf(__uint_as_float(v[c]) * rs, sc[c], bi[c]);
+      const float x1 = fmaf(__uint_as_float(v[c + 1]) * rs, sc[c + 1], bi[c + 1]);
+      pk[i] = pack_bf16(x0, x1);
+    }
+    st_shared_v4(buf + ((static_cast<uint32_t>(j) << 4) ^ sw), pk[0], pk[1], pk[2], pk[3]);
+  }
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_5d(ts->map, reinterpret_cast<const void*>(ts->stage + static_cast<size_t>(ts->buf) * 2048u),
+                 (g & 1) * e.OC, ts->x0, g >> 1, ts->y0, ts->b);
+    bulk_commit();
+  }
+  ts->buf ^= 1;
+}
+
+// (x, y, b): this thread's pixel of the gate-resolution grid; [g_begin, g_end): an even number of parity groups
+__device__ __forceinline__ void conv_epilogue_gate32(const EpiArgs& e, uint32_t taddr, int x, int y, int b, bool valid,
+                                                     int W, int H, const float (*s_par)[kMaxN], const float (&sc)[32],
+                                                     const float (&bi)[32], TmaStoreCtx* ts, int g_begin, int g_end) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t va[32], vb[32];
+  tmem_ld32_raw(taddr, va);
+  tmem_ld_wait_x32(va);
+  tmem_ld32_raw(taddr + 32u + static_cast<uint32_t>(g_begin * 32), vb);  // first group, under the gate math
+  float p = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    p = fmaf(s_par[3][c], fmaxf(fmaf(__uint_as_float(va[c]), 1.0f, s_par[2][c]), 0.0f), p);
+  p += __ldg(e.bvec);
+  const float rs = 1.0f / (1.0f + __expf(-p));
+  if (e.psi_out && g_begin == 0 && valid) e.psi_out[(static_cast<size_t>(b) * H + y) * W + x] = rs;
+  taddr += 32u;  // the groups follow the gate columns
+  const uint32_t row = smem_u32(ts->stage) + lane * 64u;
+  const uint32_t sw = ((lane >> 1) & 3u) << 4;
+  for (int g = g_begin; g < g_end; g += 2) {
+    tmem_ld_wait_x32(vb);
+    tmem_ld32_raw(taddr + static_cast<uint32_t>((g + 1) * 32), va);
+    gate32_group(vb, rs, sc, bi, e, ts, row, sw, g, lane);
+    tmem_ld_wait_x32(va);
+    if (g + 2 < g_end) tmem_ld32_raw(taddr + static_cast<uint32_t>((g + 2) * 32), vb);
+    gate32_group(va, rs, sc, bi, e, ts, row, sw, g + 1, lane);
   }
 }
 

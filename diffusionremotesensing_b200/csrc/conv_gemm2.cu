@@ -326,6 +326,18 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
 #pragma unroll
       for (int i = 0; i < 64; ++i) tr_bias[i] = s_par[1][i];
     }
+    // fused 32-channel attention gate: the result conv's folded BatchNorm in registers (conv_epilogue_gate32)
+    constexpr bool kGate = (EPI == EPI_STD && FL >= 0 && (FL & F_GATE) != 0);
+    const bool gate32 = kGate && a.store_sbc == 32 && a.n_sub == 32 && a.nsplit == 1 && e.nvec == 32 && e.oscale == 2 &&
+                        ((g_half & 1) == 0 || !a.solo);
+    float gate_sc[kGate ? 32 : 1], gate_bi[kGate ? 32 : 1];
+    if constexpr (kGate) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        gate_sc[i] = s_par[0][i];
+        gate_bi[i] = s_par[1][i];
+      }
+    }
     for (int tile0 = first_tile; tile0 < a.n_tiles; tile0 += 2 * tile_step, ++pno) {
       for (int job = 0; job < n_jobs; ++job) {
         const int pp = a.solo ? job : p;  // pipeline whose tile is drained
@@ -368,6 +380,12 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
             else
               conv_epilogue_std_ct<(FL & ~F_TR64)>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par,
                                                   s_te[kStageTe ? warp : 0], a.store_sbc ? &ts : nullptr, g_begin, g_end);
+          } else if constexpr (kGate) {
+            if (gate32)
+              conv_epilogue_gate32(e, taddr, x, y, b, valid, a.W, a.H, s_par, gate_sc, gate_bi, &ts, g_begin, g_end);
+            else
+              conv_epilogue_std_ct<FL>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par,
+                                       s_te[kStageTe ? warp : 0], a.store_sbc ? &ts : nullptr, g_begin, g_end);
           } else if constexpr (EPI == EPI_STD && FL >= 0)
             conv_epilogue_std_ct<FL>(e, taddr, x, y, b, valid, a.W, a.H, a.n_sub, oc_off, s_par,
                                      s_te[kStageTe ? warp : 0], a.store_sbc ? &ts : nullptr, g_begin, g_end);
