@@ -237,6 +237,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       // One warp-level step per A sub-tile: the warp waits for its halo tile, then one elected lane issues every
       // MMA of every tap that reads it back to back (streamed weights are waited for by the issuing lane itself).
       int kb = 0;
+#ifdef DRS_EPI_TRACE
+      int itl_n = 0;  // traced build: streamed weight units of pair 1 of CTA 0 stamped so far
+#endif
       while (kb < nkb) {
         if (valid) {
           mbar_wait(&s_afull[ar.idx], ar.phase, a.err, 2);
@@ -263,8 +266,15 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
             // streamed weights: one ring stage per unit of up to b_unit K-blocks (b_lo = offset inside the unit)
             for (int u0 = 0; u0 < cnt; u0 += a.b_unit) {
               const int nu = min(a.b_unit, cnt - u0);
+#ifdef DRS_EPI_TRACE
+              const bool itl = (a.timeline & 1) && blockIdx.x == 0 && p == 0 && pno == 1 && itl_n < 10;
+              if (itl) g_epi_trace[32 + itl_n * 3] = clock64();
+#endif
               mbar_wait(&s_bfull[br.idx], br.phase, a.err, 2);
               tc_fence_after();
+#ifdef DRS_EPI_TRACE
+              if (itl) g_epi_trace[32 + itl_n * 3 + 1] = clock64();
+#endif
               if (valid) {
                 const uint32_t bofs = b_base16 + static_cast<uint32_t>((br.idx * a.b_stage_bytes) >> 4);
                 if (K0.nk == 4)
@@ -274,6 +284,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
                 else
                   issue_resident<1>(prog, kb + u0, nu, acc, slot16, bofs);
                 umma_commit(&s_bempty[br.idx]);
+#ifdef DRS_EPI_TRACE
+                if (itl) g_epi_trace[32 + itl_n++ * 3 + 2] = clock64();
+#endif
               } else {
                 mbar_arrive(&s_bempty[br.idx]);  // no tile 1 in the last pair: release the stage unused
               }

@@ -109,6 +109,38 @@ static std::vector<Tap> taps_of(int kind) {
   return t;
 }
 
+// One K-block of a halo-tile program: the taps that read the SAME activation offset and feed CONSECUTIVE accumulator
+// column groups, stacked along N (one MMA instead of one per tap). Only the transposed convolution has such taps: of
+// its nine, the four at shift (0, 0) feed phases 0..3 (N = 4 n_sub), the two at (0, +1 row) phases 2, 3, the rest
+// stand alone - five MMAs per K slice instead of nine, the same accumulation order per output element.
+struct KRec {
+  int dx, dy, py, px;
+  std::vector<Tap> parts;  // ascending, consecutive groups
+};
+
+static std::vector<KRec> records_of(int kind, bool stack_phases) {
+  std::vector<KRec> out;
+  const std::vector<Tap> taps = taps_of(kind);
+  if (kind != CONV_T3x3_S2 || !stack_phases) {
+    for (const Tap& t : taps) out.push_back({t.dx, t.dy, t.py, t.px, {t}});
+    return out;
+  }
+  const int shifts[4][2] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}};  // (dx, dy) in the order every phase meets its taps
+  for (const auto& sh : shifts) {
+    std::vector<Tap> here;
+    for (const Tap& t : taps)
+      if (t.dx == sh[0] && t.dy == sh[1]) here.push_back(t);
+    std::sort(here.begin(), here.end(), [](const Tap& a, const Tap& b) { return a.group < b.group; });
+    for (size_t i = 0; i < here.size();) {
+      size_t j = i + 1;
+      while (j < here.size() && here[j].group == here[j - 1].group + 1) ++j;
+      out.push_back({sh[0], sh[1], 0, 0, std::vector<Tap>(here.begin() + i, here.begin() + j)});
+      i = j;
+    }
+  }
+  return out;
+}
+
 struct Builder {
   DrsModel* m;
   explicit Builder(DrsModel* mm) : m(mm) {}
@@ -565,6 +597,19 @@ struct Builder {
     };
     Conv2Prog& P = v.prog;
     memset(&P, 0, sizeof(P));
+    // phase stacking of the transposed convolution needs its four groups in one MMA (N = 4 n_sub <= 256)
+    static const bool no_stack = (getenv("DRS_V2_NO_PHASE_STACK") != nullptr);
+    bool stack_phases = !no_stack && g.n_groups == 4 && 4 * g.n_sub <= 256 && terms.size() == 1 &&
+                        terms[0].stack.size() == 1 && terms[0].kind == CONV_T3x3_S2;
+    if (stack_phases) {
+      // resident weights only: streamed, a stacked tile fills a ring stage on its own - one full / empty handshake per
+      // record instead of per four (ups.0.transform at cfg 2: 37.8 -> 38.9 us)
+      const ConvTerm& t = terms[0];
+      const int pix = g.src_ck[t.src] * 2;
+      const size_t image = static_cast<size_t>(9) * g.n_sub * pix * (t.C / g.src_ck[t.src]);
+      const size_t slot = (static_cast<size_t>(pix) * (kTile2W + 1) * (kTile2H + 1) + 1023) & ~static_cast<size_t>(1023);
+      if (image + 2 * slot > 200 * 1024) stack_phases = false;
+    }
     // pass 1: sizes and per-source constants (identical for every split)
     size_t w_image = 0;
     int max_a = 0, max_b = 0, n_kb = 0, n_st = 0;
@@ -576,13 +621,16 @@ struct Builder {
       v.halo_h[t.src] = G.hh;
       v.npy[t.src] = G.npy;
       max_a = std::max(max_a, pix * G.hw * G.hh * G.npy);
-      const int n = g.n_sub * static_cast<int>(t.stack.size());
-      const size_t tile_bytes = (static_cast<size_t>(n) * pix + 1023) & ~static_cast<size_t>(1023);
+      const int n1 = g.n_sub * static_cast<int>(t.stack.size());
       const int n_px = (t.kind == CONV_3x3_S2 || t.kind == CONV_2x2_S2) ? 2 : 1;
-      w_image += tile_bytes * taps_of(t.kind).size() * (t.C / ck);
-      n_kb += static_cast<int>(taps_of(t.kind).size()) * (t.C / ck);
+      for (const KRec& r : records_of(t.kind, stack_phases)) {
+        const int n = n1 * static_cast<int>(r.parts.size());
+        const size_t tile_bytes = (static_cast<size_t>(n) * pix + 1023) & ~static_cast<size_t>(1023);
+        w_image += tile_bytes * (t.C / ck);
+        n_kb += t.C / ck;
+        max_b = std::max(max_b, n * pix);
+      }
       n_st += n_px * (t.C / ck);
-      max_b = std::max(max_b, n * pix);
     }
     if (n_kb > kMaxKBlocks || n_st > kMaxSubTiles) return;
     v.a_slot_bytes = (max_a + 1023) & ~1023;
@@ -610,14 +658,14 @@ struct Builder {
         const uint32_t mask = static_cast<uint32_t>(pix / 16 - 1);
         const bool transposed = (t.kind == CONV_T3x3_S2);
         const int kh = (t.kind == CONV_1x1) ? 1 : (t.kind == CONV_2x2_S2 ? 2 : 3);
-        const std::vector<Tap> taps = taps_of(t.kind);
-        const int n = g.n_sub * static_cast<int>(t.stack.size());
+        const std::vector<KRec> recs = records_of(t.kind, stack_phases);
+        const int n1 = g.n_sub * static_cast<int>(t.stack.size());
         const int n_px = (t.kind == CONV_3x3_S2 || t.kind == CONV_2x2_S2) ? 2 : 1;
         for (int px = 0; px < n_px; ++px) {
           for (int c0 = 0; c0 < t.C; c0 += ck) {
-            std::vector<const Tap*> mine;
-            for (const Tap& tp : taps)
-              if (tp.px == px) mine.push_back(&tp);
+            std::vector<const KRec*> mine;
+            for (const KRec& r : recs)
+              if (r.px == px) mine.push_back(&r);
             if (mine.empty()) continue;
             if (s == 0) {
               SubTile& st = P.st[st_count++];
@@ -628,11 +676,15 @@ struct Builder {
               st.src = static_cast<uint8_t>(t.src);
             }
             for (size_t ti = 0; ti < mine.size(); ++ti) {
-              const Tap& tp = *mine[ti];
+              const KRec& tp = *mine[ti];
+              const int n = n1 * static_cast<int>(tp.parts.size());
               const int a_off = ((tp.dx - G.dx_min) + G.hw * (tp.py + G.npy * (tp.dy - G.dy_min))) * pix;
-              const int col = (t.col_slot + tp.group) * g.n_sub;
+              const int col = (t.col_slot + tp.parts[0].group) * g.n_sub;
               uint8_t flags = 0;
-              if (seen.insert(col).second) flags |= KB2_INIT;
+              // (a stacked record meets all of its groups for the first time together: the shift (0, 0) one)
+              bool first = false;
+              for (const Tap& part : tp.parts) first = seen.insert((t.col_slot + part.group) * g.n_sub).second || first;
+              if (first) flags |= KB2_INIT;
               if (ti == 0) flags |= KB2_FIRST;
               if (ti + 1 == mine.size()) flags |= KB2_LAST;
               max_col = std::max(max_col, col + n);
@@ -652,15 +704,16 @@ struct Builder {
               uint8_t* tile = m->wblob.data() + v.w_split_off + static_cast<size_t>(s) * w_image + image_off;
               image_off += (static_cast<size_t>(n) * pix + 1023) & ~static_cast<size_t>(1023);
               for (int r = 0; r < n; ++r) {
-                const WeightRef& wr = t.stack[r / g.n_sub];
+                const Tap& part = tp.parts[r / n1];
+                const WeightRef& wr = t.stack[(r % n1) / g.n_sub];
                 const int oc = s * g.n_sub + (r % g.n_sub);
                 for (int k = 0; k < ck; ++k) {
                   const int ci = wr.ci_off + c0 + k;
                   float val;
                   if (transposed)
-                    val = wr.w[((static_cast<size_t>(ci) * wr.oc + oc) * 3 + tp.ky) * 3 + tp.kx];
+                    val = wr.w[((static_cast<size_t>(ci) * wr.oc + oc) * 3 + part.ky) * 3 + part.kx];
                   else
-                    val = wr.w[((static_cast<size_t>(oc) * wr.cin_total + ci) * kh + tp.ky) * kh + tp.kx];
+                    val = wr.w[((static_cast<size_t>(oc) * wr.cin_total + ci) * kh + part.ky) * kh + part.kx];
                   uint32_t o = static_cast<uint32_t>(r * pix + k * 2);
                   o ^= ((o >> 7) & mask) << 4;
                   const uint16_t h = f32_to_bf16(val);

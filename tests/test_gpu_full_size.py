@@ -51,8 +51,11 @@ def digest(env):
 
 def test_kernel_paths_bit_identical_at_full_size(cuda_device):
     base = digest({})
+    # DRS_V2_NO_TMA_STORE also replaces the register-resident epilogues (conv_epilogue_tr64 / conv_epilogue_gate32)
+    # by the chunked one; DRS_V2_NO_PHASE_STACK issues the transposed convolutions tap by tap (nine MMAs per K slice
+    # instead of five with the phases stacked along N): same accumulation order per output element
     for env in ({"DRS_CG2": "none"}, {"DRS_CG2": "all"}, {"DRS_V2_NO_TMA_STORE": "1"}, {"DRS_V2_NO_SOLO": "1"},
-                {"DRS_V2_NO_PDL": "1", "DRS_NO_FORK": "1"}):
+                {"DRS_V2_NO_PDL": "1", "DRS_NO_FORK": "1"}, {"DRS_V2_NO_PHASE_STACK": "1"}):
         assert digest(env) == base, f"{env} changed the result"
 
 
