@@ -133,7 +133,8 @@ int launch_bicubic_up(const float* in, float* out, int B, int C, int H, int W, i
 // [ci][ky][kx][co]: the FMAs take them as constant operands, so the load/store unit only sees the activations.
 // One warp = 128 consecutive pixels, lane l owns pixels l, l + 32, l + 64, l + 96 (every global access of the warp
 // is lane-contiguous); 64 accumulators per thread, updated with packed fp32x2 FMAs (two independent IEEE fp32 FMAs
-// per instruction: same rounding as fmaf, same (ci, ky, kx) summation order as the reference's direct convolution).
+// per instruction: same rounding as fmaf, taps summed in the (ci, ky, kx) order of a direct convolution on top of
+// bias + condition feature).
 // The condition feature is channel-planar fp32 [ncond, 16, S, S].
 struct Conv0Weights {
   float w[4 * 9 * 16];
@@ -153,7 +154,7 @@ __device__ __forceinline__ void unpack2f(unsigned long long v, float& a, float& 
 }
 
 template <int CX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 conv0_kernel(const float* __restrict__ x, const __grid_constant__ Conv0Weights cw, const float* __restrict__ cond,
              __nv_bfloat16* __restrict__ out, int nb, int nx, int ncond, int S) {
   // the warp's 128 pixels x 16 channels of bf16 output (4 KiB, contiguous in global memory) are transposed through
@@ -172,12 +173,28 @@ conv0_kernel(const float* __restrict__ x, const __grid_constant__ Conv0Weights c
   const int py = static_cast<int>((i2 / S4) % S);
   const int b = static_cast<int>(i2 / (static_cast<long long>(S4) * S));
   const size_t plane = static_cast<size_t>(S) * S;
+  // The accumulators start from bias + condition feature, so the 16 condition loads are in flight together with the
+  // activation loads (one memory-latency phase per thread instead of two; the sum order is (b + cond) + taps).
   unsigned long long acc[4][8];  // [pixel][channel pair]
+  if (cond && ok) {
+    const float* cp = cond + static_cast<size_t>(b % ncond) * 16 * plane + static_cast<size_t>(py) * S + px;
 #pragma unroll
-  for (int c2 = 0; c2 < 8; ++c2) {
-    const unsigned long long b2 = pack2f(cw.b[2 * c2], cw.b[2 * c2 + 1]);
+    for (int c2 = 0; c2 < 8; ++c2) {
+      const float4 lo = __ldg(reinterpret_cast<const float4*>(cp + (2 * c2) * plane));
+      const float4 hi = __ldg(reinterpret_cast<const float4*>(cp + (2 * c2 + 1) * plane));
+      const float b0 = cw.b[2 * c2], b1 = cw.b[2 * c2 + 1];
+      acc[0][c2] = pack2f(b0 + lo.x, b1 + hi.x);
+      acc[1][c2] = pack2f(b0 + lo.y, b1 + hi.y);
+      acc[2][c2] = pack2f(b0 + lo.z, b1 + hi.z);
+      acc[3][c2] = pack2f(b0 + lo.w, b1 + hi.w);
+    }
+  } else {
 #pragma unroll
-    for (int p = 0; p < 4; ++p) acc[p][c2] = b2;
+    for (int c2 = 0; c2 < 8; ++c2) {
+      const unsigned long long b2 = pack2f(cw.b[2 * c2], cw.b[2 * c2 + 1]);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[p][c2] = b2;
+    }
   }
   const float* xin = x + static_cast<size_t>(b % nx) * CX * plane;
 #pragma unroll
@@ -213,14 +230,6 @@ conv0_kernel(const float* __restrict__ x, const __grid_constant__ Conv0Weights c
   for (int p = 0; p < 4; ++p)
 #pragma unroll
     for (int c2 = 0; c2 < 8; ++c2) unpack2f(acc[p][c2], a[p][2 * c2], a[p][2 * c2 + 1]);
-  if (cond && ok) {
-    const float* cp = cond + static_cast<size_t>(b % ncond) * 16 * plane + static_cast<size_t>(py) * S + px;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const float4 c4 = __ldg(reinterpret_cast<const float4*>(cp + c * plane));
-      a[0][c] += c4.x; a[1][c] += c4.y; a[2][c] += c4.z; a[3][c] += c4.w;
-    }
-  }
   // thread t owns bytes [128 t, 128 t + 128) of the warp's output: eight 16-byte chunks, XOR-swizzled by t & 7
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
