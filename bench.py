@@ -227,7 +227,7 @@ def aggregation_leg(model, dev, k_steps, rank, world, roofline):
     scene = T.np_rand(7, 1, 3, side, side).to(dev)
     d = D.Diffusion("cosine", model, "/nonexistent", noise_steps=k_steps + 1, device=str(dev),
                     magnification_factor=k, image_size=P * k, Degradation_type="DownBlur")
-    agg = D.split_aggregation_sampling(scene, P, stride, k, d, str(dev), patch_batch=32)
+    agg = D.split_aggregation_sampling(scene, P, stride, k, d, str(dev), patch_batch=128)
     n = len(agg.patches_lr)
     blocks = partition_blocks(n, world)
     counts = [b - a for a, b in blocks]

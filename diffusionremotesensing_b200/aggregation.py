@@ -102,7 +102,7 @@ def blend_patches(patches: torch.Tensor, infos: Sequence[Tuple[int, int, int, in
 
 
 class split_aggregation_sampling:
-    def __init__(self, img_lr, patch_size, stride, magnification_factor, diffusion_model, device, patch_batch=32):
+    def __init__(self, img_lr, patch_size, stride, magnification_factor, diffusion_model, device, patch_batch=128):
         assert stride <= patch_size
         self.img_lr = img_lr
         self.patch_size = patch_size
@@ -159,7 +159,10 @@ class split_aggregation_sampling:
         """SR patches [len(indices), C, P*k, P*k] for the given patch indices.
         The block is cut into ceil(n / patch_batch) batches of ONE size (the shorter ones are padded by repeating
         their last patch; the duplicate is dropped), so a single plan, time table and pair of CUDA graphs serve the
-        whole block (121 patches, patch_batch 32 -> 4 batches of 31). An empty block returns [0, C, P*k, P*k].
+        whole block (961 patches, patch_batch 128 -> 8 batches of 121). An empty block returns [0, C, P*k, P*k].
+        patch_batch (an extension: the reference samples patch by patch) defaults to 128: at 128 -> 256 a reverse step
+        costs 41.5 us per patch in batches of 31, 38.4 at 61 and 37.4-38.1 from 111 up (scripts/diag_batch_sweep.py;
+        ~35 MB of plan workspace per patch), and every sample() call carries ~3 ms + 0.16 ms per patch of set-up.
         noise(patch_index, step) / x_T(patch_index) inject per-patch noise (parity tests); private_rng draws from
         generators seeded by the block's first patch index instead of the global ones (sharded runs)."""
         indices = list(indices)

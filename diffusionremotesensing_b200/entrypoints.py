@@ -138,7 +138,7 @@ def prepare_scene(img: torch.Tensor) -> torch.Tensor:
 
 
 def aggregation_super_resolver(img_lr: torch.Tensor, model, diffusion: Diffusion, patch_size: int, stride: int,
-                               device, patch_batch: int = 32, *, noise=None, x_T=None) -> torch.Tensor:
+                               device, patch_batch: int = 128, *, noise=None, x_T=None) -> torch.Tensor:
     """Whole-scene super-resolution: split, sample every patch on this rank's share, gather, blend."""
     scene = (prepare_scene(img_lr) if img_lr.dim() == 3 else img_lr).to(device)
     agg = split_aggregation_sampling(scene, patch_size, stride, diffusion.magnification_factor, diffusion, device,
@@ -146,7 +146,7 @@ def aggregation_super_resolver(img_lr: torch.Tensor, model, diffusion: Diffusion
     return agg.aggregation_sampling(noise=noise, x_T=x_T)
 
 
-def launch(args, *, noise=None, x_T=None, patch_batch: int = 32) -> torch.Tensor:
+def launch(args, *, noise=None, x_T=None, patch_batch: int = 128) -> torch.Tensor:
     """Body of the reference CLI (Aggregation_Sampling.py:140-205): `args` carries the same attributes
     (snapshot_folder_path, snapshot_name, magnification_factor, inp_out_channels, noise_schedule, device,
     model_input_size, noise_steps, model_name, Degradation_type, patch_size, stride, destination_path, img_lr_path,

@@ -1,6 +1,6 @@
 """Diagnostic: ms per graph-replayed reverse step of the superres 256 x 256 plan by batch size and by whether every
 sample has its own condition image (aggregation sampling) or all share one (Diffusion.sample), plus the per-launch
-table of one batch size.  usage (GPU box): python scripts/diag_batch_sweep.py [profile_nb]"""
+table of one batch size.  usage (GPU box): [DRS_SWEEP=15,16,37,...] python scripts/diag_batch_sweep.py [profile_nb]"""
 import os, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -15,7 +15,9 @@ d = D.Diffusion("cosine", m, "/nonexistent", noise_steps=1500, device="cuda:0", 
                 Degradation_type="DownBlur")
 c1, c2, c3 = d._coefficients()
 S, K = 256, 30
-for nb, ncond in ((16, 1), (16, 16), (30, 30), (31, 31), (32, 32), (32, 1), (31, 1)):
+SIZES = os.environ.get("DRS_SWEEP")
+pairs = [(int(v), int(v)) for v in SIZES.split(",")] if SIZES else ((16, 1), (16, 16), (30, 30), (31, 31), (32, 32), (32, 1), (31, 1))
+for nb, ncond in pairs:
     plan = m.native_plan(nb, nb, ncond, S, 2)
     cond = T.np_rand(2, ncond, 3, S // 2, S // 2).to(dev)
     x = T.np_randn(3, nb, 3, S, S).to(dev); z = torch.empty_like(x); eps = torch.empty_like(x)
