@@ -54,8 +54,8 @@ if any(tr):
 it = [buf[256 + 32 + i] for i in range(30)]
 if any(it):
     base = min(v for v in it if v > 0)
-    print("issuer 0 trace, pair 3 (per K-block: start, after B wait + MMA issue, after commit):")
+    print("issuer 0 trace, pair 1, streamed weights (per ring unit: before the B wait, after it, after MMA issue + commit; -DDRS_EPI_TRACE builds):")
     for k in range(10):
         row = it[k * 3:k * 3 + 3]
         if any(row):
-            print(f"  kb {k:2d}: " + " ".join(f"{(v - base) if v else -1:7d}" for v in row))
+            print(f"  unit {k:2d}: " + " ".join(f"{(v - base) if v else -1:7d}" for v in row))
