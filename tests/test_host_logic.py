@@ -260,3 +260,42 @@ def test_bench_clock_sampler_filters_samples_to_the_timed_region(tmp_path):
         f.write(f"{stamp}, 1500, 1965, Not Active, Not Active, Not Active, Not Active\n")
     out = sampler().stop(t0 + 1.0, t0 + 1.001)
     assert out["samples"] == 1 and out["sm_mhz"] == 1500 and out["window"].startswith("whole run")
+
+
+def test_default_patch_batching_at_the_cfg5_shape():
+    """961 patches (LR 2048 x 2048, patch 128, stride 64) with the default patch_batch: 8 equal batches of 121 on one
+    rank (7 padded duplicates dropped), one batch of 120 / 121 per rank on eight."""
+
+    class Stub:
+        model = None
+        calls = []
+
+        def sample_batched(self, model, lr, input_channels=3, **kw):
+            Stub.calls.append(lr.shape[0])
+            return torch.zeros(lr.shape[0], 3, 4, 4)
+
+    agg = D.split_aggregation_sampling(torch.zeros(1, 3, 2048, 2048), 128, 64, 2, Stub(), "cpu")
+    assert len(agg.patches_lr) == 961 and agg.patch_batch == 128
+    # the stub returns 4 x 4 "patches": only the batching arithmetic is under test
+    agg.patch_size = 2
+    out = agg.sample_patches(range(961))
+    assert out.shape[0] == 961 and Stub.calls == [121] * 8
+    for lo, hi in D.partition_blocks(961, 8):
+        Stub.calls.clear()
+        assert agg.sample_patches(range(lo, hi)).shape[0] == hi - lo
+        assert Stub.calls == [hi - lo]
+
+
+def test_committed_ncu_traffic_follows_from_the_committed_capture():
+    """bench.py's roofline.traffic comes from profiles/ncu_traffic.json: it must be what profiles/make_ncu_traffic.py
+    derives from the committed conv-chain capture."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(T.ROOT, "profiles", "make_ncu_traffic.py"),
+                          os.path.join("profiles", "ncu_r2_conv_chain_full.csv")], cwd=T.ROOT, capture_output=True,
+                         text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    want = json.loads(out.stdout)
+    have = json.load(open(os.path.join(T.ROOT, "profiles", "ncu_traffic.json")))
+    assert have["launches"] == want["launches"] == 28
+    for k in ("dram_bytes_per_launch", "dram_read_bytes_per_eval", "dram_write_bytes_per_eval"):
+        assert abs(have[k] - want[k]) <= 1e-6 * want[k], k
