@@ -79,7 +79,8 @@ __device__ __forceinline__ void issue_resident(const Conv2Prog& prog, int kb, in
 constexpr int kMmaWarp0 = 8;      // issuer of tile 0 of a pair (tile 1: kMmaWarp0 + 1)
 constexpr int kProducerWarp = 10;
 
-// FL: EPI_STD flag word known at compile time (the seven combinations the UNets use), or -1 for the generic epilogue.
+// FL: EPI_STD flag word known at compile time (the combinations the UNets use: DRS_GEMM2_VARIANTS), or -1 for the
+// generic epilogue.
 template <int EPI, int FL>
 __global__ void __launch_bounds__(kGemm2Threads)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
